@@ -1,0 +1,313 @@
+"""ctypes binding of libfcpb200.so (declared in include/fcp_b200.h).
+
+There is NO CPU fallback: importing works anywhere (so CPU-only tooling can inspect the package), but creating a
+:class:`Context` without the built library or without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = Path(os.environ.get("FCP_B200_LIB", _HERE / "libfcpb200.so"))
+
+OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_CAPACITY = 0, 1, 2, 3, 4
+MODEL_RETINAFACE, MODEL_BISENET, MODEL_RRDBNET = 0, 1, 2
+STRATEGIES = {"all": 0, "best": 1, "largest": 2}
+BORDERS = {"constant": 0, "replicate": 1, "reflect": 2, "wrap": 3, "reflect_101": 4}
+ACTS = {"none": 0, "relu": 1, "lrelu": 2, "sigmoid": 3}
+
+_p = C.c_void_p
+_i = C.c_int
+_f = C.c_float
+
+#: every symbol include/fcp_b200.h declares -> (restype, argtypes)
+SIGNATURES = {
+    "fcp_create": (_i, [_i, C.POINTER(_p)]),
+    "fcp_destroy": (None, [_p]),
+    "fcp_last_error": (C.c_char_p, [_p]),
+    "fcp_version": (C.c_char_p, []),
+    "fcp_set_stream": (_i, [_p, _p]),
+    "fcp_sync": (_i, [_p]),
+    "fcp_launch_count": (C.c_int64, [_p]),
+    "fcp_set_micro_batch": (_i, [_p, _i, _i]),
+    "fcp_set_conv_impl": (_i, [_p, _i]),
+    "fcp_load_tensor": (_i, [_p, _i, C.c_char_p, _p, C.POINTER(C.c_int64), _i]),
+    "fcp_finalize": (_i, [_p, _i, _i]),
+    "fcp_detect": (_i, [_p, _p, _i, _i, _i, _f, _f, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "fcp_detect_heads": (_i, [_p, _p, _i, _i, _i, _p]),
+    "fcp_detect_post": (_i, [_p, _p, _i, _i, _i, _f, _f, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "fcp_align": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _i, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "fcp_align_list": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _i, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "fcp_parse": (_i, [_p, _p, _i, _i, _i, _p, _p]),
+    "fcp_parse_logits": (_i, [_p, _p, _i, _i, _i, _p]),
+    "fcp_parse_tail": (_i, [_p, _p, _i, _i, _i, _p, _p]),
+    "fcp_masks": (_i, [_p, _p, _i, _i, _i, _p, _p]),
+    "fcp_enhance": (_i, [_p, _p, _i, _i, _i, _p]),
+    "fcp_enhance_forward": (_i, [_p, _p, _i, _i, _i, _p]),
+    "fcp_pipeline": (_i, [_p, _p, _i, _i, _i, _p, _f, _f, _i, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "fcp_conv2d": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _p, _p, _p, _i, _f, _i, _p]),
+}
+
+_lib = None
+
+
+class FcpError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libfcpb200 error {code}: {message}")
+        self.code = code
+
+
+def load_library() -> C.CDLL:
+    """Loads libfcpb200.so and declares the prototypes; raises if the library was not built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m face_crop_plus_b200.build` "
+                               "(there is no CPU fallback)")
+        lib = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def _ptr(x):
+    """Pointer of a numpy array, a torch tensor (host or CUDA), an int address, or None."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        assert x.flags["C_CONTIGUOUS"], "arrays crossing the C ABI must be C-contiguous"
+        return x.ctypes.data
+    if hasattr(x, "data_ptr"):
+        assert x.is_contiguous(), "tensors crossing the C ABI must be contiguous"
+        return x.data_ptr()
+    return int(x)
+
+
+class Context:
+    """One libfcpb200 context = one CUDA device + one stream + the loaded models."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = _p()
+        code = self.lib.fcp_create(int(device), C.byref(h))
+        if code != OK:
+            raise FcpError(code, f"fcp_create(device={device}) failed — a CUDA device is required, there is no CPU fallback")
+        self.h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.fcp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, code: int, allow=()):
+        if code != OK and code not in allow:
+            raise FcpError(code, self.lib.fcp_last_error(self.h).decode())
+        return code
+
+    # ---- plumbing
+    def version(self) -> str:
+        return self.lib.fcp_version().decode()
+
+    def set_stream(self, cuda_stream: int):
+        self.check(self.lib.fcp_set_stream(self.h, cuda_stream))
+
+    def sync(self):
+        self.check(self.lib.fcp_sync(self.h))
+
+    def launch_count(self) -> int:
+        return int(self.lib.fcp_launch_count(self.h))
+
+    def set_micro_batch(self, detect_images: int, parse_faces: int):
+        self.check(self.lib.fcp_set_micro_batch(self.h, detect_images, parse_faces))
+
+    def set_conv_impl(self, impl: int):
+        self.check(self.lib.fcp_set_conv_impl(self.h, impl))
+
+    def load_state_dict(self, model: int, state_dict, rrdb_blocks: int = 23):
+        """Feeds a reference-format state_dict (torch tensors or numpy arrays) and finalizes the model."""
+        for key, value in state_dict.items():
+            if key.endswith("num_batches_tracked"):
+                continue
+            arr = value.detach().cpu().numpy() if hasattr(value, "detach") else np.asarray(value)
+            arr = np.ascontiguousarray(arr, dtype=np.float32)
+            shape = (C.c_int64 * max(arr.ndim, 1))(*arr.shape)
+            self.check(self.lib.fcp_load_tensor(self.h, model, key.encode(), arr.ctypes.data, shape, arr.ndim))
+        self.check(self.lib.fcp_finalize(self.h, model, rrdb_blocks))
+
+    # ---- detect
+    def _det_outputs(self, cap):
+        return (np.empty((cap, 5, 2), np.float32), np.empty(cap, np.int32), np.empty((cap, 4), np.float32),
+                np.empty(cap, np.float32), np.empty(cap, np.int32), np.zeros(1, np.int32))
+
+    def detect(self, images, vis_threshold=0.6, nms_threshold=0.4, strategy="all", max_faces=None, n=None, h=None, w=None):
+        """images: u8 [n,h,w,3] numpy array or CUDA tensor.  Returns dict(landmarks, indices, boxes, scores, anchors)."""
+        if n is None:
+            n, h, w = images.shape[:3]
+        cap = max_faces or (n if strategy != "all" else max(64 * n, 1024))
+        while True:
+            lm, idx, box, sc, an, cnt = self._det_outputs(cap)
+            code = self.lib.fcp_detect(self.h, _ptr(images), n, h, w, vis_threshold, nms_threshold, STRATEGIES[strategy],
+                                       cap, _ptr(lm), _ptr(idx), _ptr(box), _ptr(sc), _ptr(an), _ptr(cnt))
+            self.check(code, allow=(ERR_CAPACITY,))
+            if code == OK:
+                k = int(cnt[0])
+                return dict(landmarks=lm[:k], indices=idx[:k], boxes=box[:k], scores=sc[:k], anchors=an[:k])
+            cap = int(cnt[0])
+
+    def detect_heads(self, images):
+        n, h, w = images.shape[:3]
+        a = num_priors(h, w)
+        out = np.empty((n, a, 16), np.float32)
+        self.check(self.lib.fcp_detect_heads(self.h, _ptr(images), n, h, w, _ptr(out)))
+        return out
+
+    def detect_post(self, heads, h, w, vis_threshold=0.6, nms_threshold=0.4, strategy="all", max_faces=None):
+        heads = np.ascontiguousarray(heads, dtype=np.float32)
+        n = heads.shape[0]
+        cap = max_faces or (n if strategy != "all" else max(64 * n, 1024))
+        while True:
+            lm, idx, box, sc, an, cnt = self._det_outputs(cap)
+            code = self.lib.fcp_detect_post(self.h, _ptr(heads), n, h, w, vis_threshold, nms_threshold, STRATEGIES[strategy],
+                                            cap, _ptr(lm), _ptr(idx), _ptr(box), _ptr(sc), _ptr(an), _ptr(cnt))
+            self.check(code, allow=(ERR_CAPACITY,))
+            if code == OK:
+                k = int(cnt[0])
+                return dict(landmarks=lm[:k], indices=idx[:k], boxes=box[:k], scores=sc[:k], anchors=an[:k])
+            cap = int(cnt[0])
+
+    # ---- align
+    def align(self, images, paddings, indices, landmarks, target, out_size=(256, 256), border="constant", allow_skew=False):
+        """images: u8 [n,h,w,3] array, or a list of u8 [h_i,w_i,3] arrays.  Returns (crops, matrices, valid)."""
+        f = len(indices)
+        ow, oh = int(out_size[0]), int(out_size[1])
+        crops = np.empty((f, oh, ow, 3), np.uint8)
+        mats = np.empty((f, 2, 3), np.float64)
+        valid = np.zeros(f, np.uint8)
+        idx = np.ascontiguousarray(indices, dtype=np.int32)
+        lms = np.ascontiguousarray(landmarks, dtype=np.float32).reshape(f, 5, 2)
+        tgt = np.ascontiguousarray(target, dtype=np.float32)
+        pad = None if paddings is None else np.ascontiguousarray(paddings, dtype=np.int32)
+        bm = BORDERS[border] if isinstance(border, str) else int(border)
+        if isinstance(images, (list, tuple)):
+            imgs = [np.ascontiguousarray(im) for im in images]
+            n = len(imgs)
+            ptrs = (C.c_void_p * max(n, 1))(*[im.ctypes.data for im in imgs])
+            hs = np.array([im.shape[0] for im in imgs], np.int32)
+            ws = np.array([im.shape[1] for im in imgs], np.int32)
+            self.check(self.lib.fcp_align_list(self.h, C.cast(ptrs, _p), _ptr(hs), _ptr(ws), n, _ptr(pad), _ptr(idx), _ptr(lms),
+                                               f, _ptr(tgt), ow, oh, bm, int(allow_skew), _ptr(crops), _ptr(mats), _ptr(valid)))
+        else:
+            n, h, w = images.shape[:3]
+            self.check(self.lib.fcp_align(self.h, _ptr(images), n, h, w, _ptr(pad), _ptr(idx), _ptr(lms), f, _ptr(tgt), ow, oh,
+                                          bm, int(allow_skew), _ptr(crops), _ptr(mats), _ptr(valid)))
+        return crops, mats, valid.astype(bool)
+
+    # ---- parse
+    def parse(self, crops):
+        f, h, w = crops.shape[:3]
+        labels = np.empty((f, h, w), np.uint8)
+        hist = np.zeros((f, 19), np.int32)
+        self.check(self.lib.fcp_parse(self.h, _ptr(crops), f, h, w, _ptr(labels), _ptr(hist)))
+        return labels, hist
+
+    def parse_logits(self, crops):
+        f, h, w = crops.shape[:3]
+        out = np.empty((f, 19, 64, 64), np.float32)
+        self.check(self.lib.fcp_parse_logits(self.h, _ptr(crops), f, h, w, _ptr(out)))
+        return out
+
+    def parse_tail(self, logits, h, w):
+        logits = np.ascontiguousarray(logits, dtype=np.float32)
+        f = logits.shape[0]
+        labels = np.empty((f, h, w), np.uint8)
+        hist = np.zeros((f, 19), np.int32)
+        self.check(self.lib.fcp_parse_tail(self.h, _ptr(logits), f, h, w, _ptr(labels), _ptr(hist)))
+        return labels, hist
+
+    def masks(self, labels, classes):
+        labels = np.ascontiguousarray(labels, dtype=np.uint8)
+        f, h, w = labels.shape
+        lut = np.zeros(19, np.uint8)
+        lut[[c for c in classes if 0 <= c < 19]] = 1
+        out = np.empty((f, h, w), np.uint8)
+        self.check(self.lib.fcp_masks(self.h, _ptr(labels), f, h, w, _ptr(lut), _ptr(out)))
+        return out
+
+    # ---- enhance
+    def enhance(self, images_nchw, gate=None):
+        """In place on a float32 [n,3,h,w] numpy array or CUDA tensor."""
+        n, _, h, w = images_nchw.shape
+        g = None if gate is None else np.ascontiguousarray(gate, dtype=np.uint8)
+        self.check(self.lib.fcp_enhance(self.h, _ptr(images_nchw), n, h, w, _ptr(g)))
+        return images_nchw
+
+    def enhance_forward(self, x_nchw):
+        x = np.ascontiguousarray(x_nchw, dtype=np.float32)
+        n, _, h, w = x.shape
+        out = np.empty((n, 3, 4 * h, 4 * w), np.float32)
+        self.check(self.lib.fcp_enhance_forward(self.h, _ptr(x), n, h, w, _ptr(out)))
+        return out
+
+    # ---- whole path
+    def pipeline(self, images, paddings, target, out_size=(256, 256), vis_threshold=0.6, nms_threshold=0.4,
+                 strategy="largest", border="constant", allow_skew=False, parse=True, max_faces=None, out=None,
+                 n=None, h=None, w=None):
+        """detect -> un-pad -> align -> parse in one call.  ``images``/``out`` buffers may be numpy (host) or CUDA tensors."""
+        if n is None:
+            n, h, w = images.shape[:3]
+        ow, oh = int(out_size[0]), int(out_size[1])
+        cap = max_faces or (n if strategy != "all" else max(64 * n, 1024))
+        tgt = np.ascontiguousarray(target, dtype=np.float32)
+        pad = None if paddings is None else np.ascontiguousarray(paddings, dtype=np.int32)
+        bm = BORDERS[border] if isinstance(border, str) else int(border)
+        while True:
+            o = out or dict(landmarks=np.empty((cap, 5, 2), np.float32), indices=np.empty(cap, np.int32),
+                            crops=np.empty((cap, oh, ow, 3), np.uint8), matrices=np.empty((cap, 2, 3), np.float64),
+                            valid=np.zeros(cap, np.uint8), labels=np.empty((cap, oh, ow), np.uint8) if parse else None,
+                            hist=np.zeros((cap, 19), np.int32) if parse else None)
+            cnt = np.zeros(1, np.int32)
+            code = self.lib.fcp_pipeline(self.h, _ptr(images), n, h, w, _ptr(pad), vis_threshold, nms_threshold,
+                                         STRATEGIES[strategy], _ptr(tgt), ow, oh, bm, int(allow_skew), cap,
+                                         _ptr(o["landmarks"]), _ptr(o["indices"]), _ptr(cnt), _ptr(o["crops"]),
+                                         _ptr(o.get("matrices")), _ptr(o.get("valid")), _ptr(o.get("labels")), _ptr(o.get("hist")))
+            self.check(code, allow=(ERR_CAPACITY,))
+            if code == OK:
+                k = int(cnt[0])
+                res = {key: (val[:k] if val is not None else None) for key, val in o.items()}
+                res["count"] = k
+                return res
+            if out is not None:
+                raise FcpError(code, "caller-provided output buffers are too small")
+            cap = int(cnt[0])
+
+    # ---- kernel test hook
+    def conv2d(self, x_nhwc, weight_oihw, stride=1, pad=0, scale=None, shift=None, residual=None, act="none", slope=0.0, impl=0):
+        x = np.ascontiguousarray(x_nhwc, dtype=np.float32)
+        wt = np.ascontiguousarray(weight_oihw, dtype=np.float32)
+        n, h, w, cin = x.shape
+        cout, _, k, _ = wt.shape
+        ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+        out = np.empty((n, ho, wo, cout), np.float32)
+        f32 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+        scale, shift, residual = f32(scale), f32(shift), f32(residual)
+        self.check(self.lib.fcp_conv2d(self.h, _ptr(x), n, h, w, cin, _ptr(wt), cout, k, stride, pad, _ptr(scale), _ptr(shift),
+                                       _ptr(residual), ACTS[act], slope, impl, _ptr(out)))
+        return out
+
+
+def num_priors(h: int, w: int) -> int:
+    """Number of RetinaFace priors for an h x w input (PriorBox, _layers.py:41-62)."""
+    return sum(2 * -(-h // s) * -(-w // s) for s in (8, 16, 32))

@@ -1,0 +1,196 @@
+// Internal declarations shared by the runtime and the kernels of libfcpb200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/fcp_b200.h"
+
+namespace fcp {
+
+// ----------------------------------------------------------------------------------------------------------
+// activation tensor view: NHWC float32; `cs` is the channel stride of the underlying buffer (>= c) and `co`
+// the channel offset of this view inside it, so concatenations are written in place (cat-free).
+// ----------------------------------------------------------------------------------------------------------
+struct Tensor {
+    float* p = nullptr;
+    int n = 0, h = 0, w = 0, c = 0;
+    int cs = 0, co = 0;
+    size_t pixels() const { return (size_t)n * h * w; }
+    Tensor slice(int off, int count) const {
+        Tensor t = *this;
+        t.co = co + off;
+        t.c = count;
+        return t;
+    }
+};
+
+// ----------------------------------------------------------------------------------------------------------
+// one fused convolution: out = post(act(conv(in) * scale + shift + res1)) ...
+// ----------------------------------------------------------------------------------------------------------
+struct ConvWeights {
+    int cout = 0, cin = 0, k = 1;
+    int cout_pad = 0;          // columns of the packed matrix (multiple of 32)
+    float* w_kn = nullptr;     // device [k*k*cin][cout_pad]  (row = (r*k+s)*cin + c), CUDA-core kernel
+    float* w_hi = nullptr;     // device [cout_pad][k*k*cin] K-major, tf32-truncated part   (tcgen05 kernel)
+    float* w_lo = nullptr;     // device [cout_pad][k*k*cin] K-major, residual part          (tcgen05 kernel)
+    float* scale = nullptr;    // device [cout_pad]
+    float* shift = nullptr;    // device [cout_pad]
+};
+
+struct ConvOp {
+    Tensor in, out;
+    const ConvWeights* wt = nullptr;
+    int stride = 1, pad = 0;
+    int up_in = 0;             // read the input through a nearest x2 upsample (logical size = 2x physical)
+    int act = FCP_ACT_NONE;
+    float slope = 0.f;
+    const float* res1 = nullptr; int res1_cs = 0, res1_co = 0;              // added before the activation
+    float post_scale = 1.f;
+    const float* res2 = nullptr; int res2_cs = 0, res2_co = 0;              // added after act*post_scale
+    int res2_h = 0, res2_w = 0;                                             // != 0: res2 is [n,res2_h,res2_w,*], read through a nearest resize
+    float post_scale2 = 1.f;
+    const float* res3 = nullptr; int res3_cs = 0, res3_co = 0;              // added after (..)*post_scale2
+    int impl = 0;              // 0 CUDA-core fp32, 1 tcgen05 3xTF32
+};
+
+// ----------------------------------------------------------------------------------------------------------
+// simple stream-ordered arena: first-fit free list over one big cudaMalloc
+// ----------------------------------------------------------------------------------------------------------
+class Arena {
+public:
+    ~Arena();
+    bool reserve(size_t bytes);           // (re)allocates the slab if it is smaller than `bytes`
+    void* alloc(size_t bytes);            // returns nullptr when exhausted
+    void free(void* p);
+    void reset();
+    void set_plan_mode(bool on);          // plan mode: unlimited virtual space, fake addresses, records high_water
+    bool plan_mode() const { return plan_; }
+    size_t capacity() const { return cap_; }
+    size_t high_water() const { return high_; }
+private:
+    struct Block { size_t off, size; bool used; };
+    char* base_ = nullptr;
+    size_t cap_ = 0, high_ = 0;
+    bool plan_ = false;
+    std::vector<Block> blocks_;
+};
+
+struct HostTensor {
+    std::vector<float> data;
+    std::vector<int64_t> shape;
+};
+
+struct Model {
+    std::map<std::string, HostTensor> host;          // as fed by fcp_load_tensor
+    std::map<std::string, ConvWeights> conv;         // finalized (folded + packed) convolutions by name
+    std::map<std::string, std::vector<float>> vec;   // small host-side vectors (e.g. folded BN for 1x1 GEMVs)
+    bool finalized = false;
+    int rrdb_blocks = 23;
+};
+
+}  // namespace fcp
+
+struct fcp_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string error;
+    int64_t launches = 0;
+    int det_mb = 8, par_mb = 32;
+    fcp::Model models[3];
+    fcp::Arena arena;          // activations
+    fcp::Arena scratch;        // staging of host inputs/outputs, candidate buffers
+    std::vector<void*> device_allocs;   // weights etc. freed at destroy
+    void* pinned = nullptr; size_t pinned_bytes = 0;
+    int sm_count = 148;
+    int use_tc = 0;            // default conv implementation for the model graphs (0 ffma, 1 tcgen05)
+};
+
+namespace fcp {
+
+int fail(fcp_ctx* ctx, int code, const std::string& msg);
+
+#define FCP_CUDA(ctx, expr)                                                                            \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess)                                                                         \
+            return fcp::fail(ctx, FCP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));   \
+    } while (0)
+
+#define FCP_TRY(expr)                  \
+    do {                               \
+        int _s = (expr);               \
+        if (_s != FCP_OK) return _s;   \
+    } while (0)
+
+#define FCP_KERNEL_CHECK(ctx)                                                                          \
+    do {                                                                                               \
+        (ctx)->launches++;                                                                             \
+        cudaError_t _e = cudaGetLastError();                                                           \
+        if (_e != cudaSuccess)                                                                         \
+            return fcp::fail(ctx, FCP_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(_e)); \
+    } while (0)
+
+// ---- kernels (one launcher per .cu) -----------------------------------------------------------------------
+int launch_conv_ffma(fcp_ctx* ctx, const ConvOp& op);
+int launch_conv_tc(fcp_ctx* ctx, const ConvOp& op);
+int run_conv(fcp_ctx* ctx, const ConvOp& op);
+
+// stem: 7x7/s2 conv (Cin=3 -> 64) + scale/shift + ReLU.  mode 0: src = u8 RGB NHWC, flipped to BGR and mean-subtracted
+// (retinaface.py:450-451); mode 1: src = f32 NHWC 3-channel
+int launch_stem7(fcp_ctx* ctx, const void* src, int mode, int n, int h, int w, const float* w_kn /*[147][64]*/,
+                 const float* scale, const float* shift, Tensor out);
+// conv 3x3/s1 with Cin=3 (RRDB conv_first): f32 NCHW input scaled by in_scale, + bias
+int launch_conv3_first(fcp_ctx* ctx, const float* src_nchw, float in_scale, int n, int h, int w, const float* w_kn,
+                       const float* shift, Tensor out);
+int launch_maxpool3s2(fcp_ctx* ctx, Tensor in, Tensor out);
+int launch_global_avgpool(fcp_ctx* ctx, Tensor in, float* out_nc);                     // out[n][c] = mean_hw
+// out[n][co] = act((sum_ci in[n][ci] * w[ci][co]) * scale[co] + shift[co])           (1x1 conv on a pooled vector)
+int launch_fc(fcp_ctx* ctx, const float* in_nc, int n, int cin, const ConvWeights* wt, int act, float* out_nc);
+// out = in * mul[n][c] (+ addvec[n][c]) (+ in) (+ addt nearest-upsampled by up): channel attention / fusion ops
+int launch_channel_affine(fcp_ctx* ctx, Tensor in, const float* mul_nc, const float* addvec_nc, int add_self,
+                          Tensor out);
+
+// detection post-processing (det_post.cu)
+int det_num_priors(int h, int w);
+int det_key_capacity(int h, int w);
+int launch_heads_to_flat(fcp_ctx* ctx, const float* const* level_ptrs, int n, int h, int w, float* out_heads);
+// decode+threshold -> per-image sort+NMS+strategy -> image-ordered append of the kept faces at faces[*face_count...]
+// (face_count must be zeroed before the first micro-batch; img_base = batch index of this micro-batch's image 0)
+int launch_det_post(fcp_ctx* ctx, const float* const* level_ptrs, const float* heads_flat, int n, int img_base, int h,
+                    int w, float vis_thr, float nms_thr, int strategy, int max_faces, float* rec,
+                    unsigned long long* keys, unsigned char* supp, int32_t* cand_count, int32_t* kept_count,
+                    float* faces, int32_t* face_img, int32_t* face_count);
+// faces[f][16] records -> landmarks [f][10] (minus (left, top) of paddings[img]), boxes, scores, anchors
+int launch_unpack_faces(fcp_ctx* ctx, const float* faces, const int32_t* face_img, const int32_t* face_count, int cap,
+                        const int32_t* paddings, float* landmarks, float* boxes, float* scores, int32_t* anchors);
+
+// align (align.cu)
+int launch_solve(fcp_ctx* ctx, const float* landmarks, const int32_t* face_count_dev, int f, const float* target,
+                 int allow_skew, double* matrices, double* inv, uint8_t* valid);
+int launch_invert(fcp_ctx* ctx, const double* matrices, int f, double* inv);
+int launch_warp(fcp_ctx* ctx, const uint8_t* images, int n, int h, int w, const uint8_t* const* image_ptrs,
+                const int32_t* hs, const int32_t* ws, const int32_t* paddings, const int32_t* indices,
+                const int32_t* face_count_dev, int f, const double* inv, const uint8_t* valid, int out_w, int out_h,
+                int border, uint8_t* out);
+
+// parse
+int launch_parse_prep(fcp_ctx* ctx, const uint8_t* crops, int f, int h, int w, float* out_nhwc3 /*[f,512,512,3]*/);
+int launch_parse_tail(fcp_ctx* ctx, const float* logits, int layout_nhwc, int cs, int f, int fh, int fw, int h, int w,
+                      uint8_t* labels, int32_t* hist);
+int launch_masks(fcp_ctx* ctx, const uint8_t* labels, size_t count, const uint8_t* lut_dev, uint8_t* out);
+int launch_nhwc_to_nchw(fcp_ctx* ctx, const float* in, int n, int h, int w, int c, int cs, float* out);
+
+// enhance tail: conv_last output [n,4h,4w,3(+pad)] -> bicubic x0.25 -> clamp*255 round, written NCHW f32 [3,h,w]
+int launch_rrdb_tail(fcp_ctx* ctx, Tensor x4, float* out_nchw, int h, int w);
+
+// model graphs (runtime.cu)
+int finalize_retinaface(fcp_ctx* ctx);
+int finalize_bisenet(fcp_ctx* ctx);
+int finalize_rrdbnet(fcp_ctx* ctx);
+
+}  // namespace fcp

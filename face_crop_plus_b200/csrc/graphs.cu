@@ -1,0 +1,880 @@
+// graphs.cu — the three network graphs (RetinaFace, BiSeNet, RRDBNet) expressed over the fused conv kernel and the
+// small kernels of misc.cu, plus the C-ABI entry points that run them (detect / align / parse / enhance / pipeline).
+//
+// Graph structure follows the reference modules op for op (file:line cited at each block); what changes is the
+// execution: NHWC float32 activations, BatchNorm folded into the conv epilogue, concatenations written in place
+// through channel-offset views, nearest upsampling read through index arithmetic, residual adds in epilogues.
+#include <algorithm>
+#include <functional>
+
+#include "graphs.h"
+
+namespace fcp {
+
+static inline int odim(int in, int k, int s, int p) { return (in + 2 * p - k) / s + 1; }
+
+// ------------------------------------------------------------------------------------------------------- Exec
+Tensor Exec::alloc(int n, int h, int w, int c, int cs) {
+    Tensor t;
+    t.n = n; t.h = h; t.w = w; t.c = c; t.cs = cs ? cs : c; t.co = 0;
+    if (!ok()) return t;
+    t.p = static_cast<float*>(ctx->arena.alloc(t.pixels() * t.cs * sizeof(float)));
+    if (!t.p) status = fail(ctx, FCP_ERR_CUDA, "activation arena exhausted");
+    return t;
+}
+float* Exec::alloc_vec(size_t count) {
+    if (!ok()) return nullptr;
+    float* p = static_cast<float*>(ctx->arena.alloc(count * sizeof(float)));
+    if (!p) status = fail(ctx, FCP_ERR_CUDA, "activation arena exhausted");
+    return p;
+}
+void Exec::free(Tensor& t) {
+    if (t.p && t.co == 0) ctx->arena.free(t.p);
+    t.p = nullptr;
+}
+void Exec::free_vec(float* p) { ctx->arena.free(p); }
+
+const ConvWeights* Exec::W(const std::string& name) {
+    auto it = model->conv.find(name);
+    if (it == model->conv.end()) {
+        if (ok()) status = fail(ctx, FCP_ERR_STATE, "conv not finalized: " + name);
+        return nullptr;
+    }
+    return &it->second;
+}
+
+bool Exec::conv(const std::string& name, Tensor in, Tensor out, int stride, int pad, int act, ConvOp extra) {
+    if (!ok()) return false;
+    const ConvWeights* wt = W(name);
+    if (!wt) return false;
+    ConvOp op = extra;
+    op.in = in; op.out = out; op.wt = wt; op.stride = stride; op.pad = pad; op.act = act;
+    op.impl = ctx->use_tc;
+    if (dry) return true;
+    status = run_conv(ctx, op);
+    return ok();
+}
+
+static ConvOp with_res1(Tensor r) {
+    ConvOp e;
+    e.res1 = r.p; e.res1_cs = r.cs; e.res1_co = r.co;
+    return e;
+}
+
+// =========================================================================================== RetinaFace graph
+int finalize_retinaface(fcp_ctx* ctx) {
+    Model& m = ctx->models[FCP_MODEL_RETINAFACE];
+    FCP_TRY(pack_conv(ctx, m, {"body.conv1"}, "body.bn1", "body.conv1"));
+    const int blocks[4] = {3, 4, 6, 3};
+    for (int li = 1; li <= 4; ++li)
+        for (int b = 0; b < blocks[li - 1]; ++b) {
+            std::string p = "body.layer" + std::to_string(li) + "." + std::to_string(b);
+            for (int c = 1; c <= 3; ++c)
+                FCP_TRY(pack_conv(ctx, m, {p + ".conv" + std::to_string(c)}, p + ".bn" + std::to_string(c), p + ".conv" + std::to_string(c)));
+            if (b == 0) FCP_TRY(pack_conv(ctx, m, {p + ".downsample.0"}, p + ".downsample.1", p + ".downsample"));
+        }
+    for (const char* n : {"fpn.output1", "fpn.output2", "fpn.output3", "fpn.merge1", "fpn.merge2"})
+        FCP_TRY(pack_conv(ctx, m, {std::string(n) + ".0"}, std::string(n) + ".1", n));
+    for (int s = 1; s <= 3; ++s)
+        for (const char* n : {"conv3X3", "conv5X5_1", "conv5X5_2", "conv7X7_2", "conv7x7_3"}) {
+            std::string p = "ssh" + std::to_string(s) + "." + n;
+            FCP_TRY(pack_conv(ctx, m, {p + ".0"}, p + ".1", p));
+        }
+    for (int i = 0; i < 3; ++i) {
+        std::string s = std::to_string(i);
+        // the three 1x1 heads of a level share their input: one 256->32 conv = (cls 4 | box 8 | ldm 20) (_layers.py:147-162)
+        FCP_TRY(pack_conv(ctx, m, {"ClassHead." + s + ".conv1x1", "BboxHead." + s + ".conv1x1", "LandmarkHead." + s + ".conv1x1"},
+                          "", "heads." + s));
+    }
+    return FCP_OK;
+}
+
+// torchvision Bottleneck (resnet.py:143-163): 1x1 -> 3x3(stride) -> 1x1, BN each, residual add, ReLU
+static Tensor bottleneck(Exec& ex, const std::string& p, Tensor x, int planes, int stride, bool down) {
+    int ho = odim(x.h, 3, stride, 1), wo = odim(x.w, 3, stride, 1);
+    Tensor t1 = ex.alloc(x.n, x.h, x.w, planes);
+    ex.conv(p + ".conv1", x, t1, 1, 0, FCP_ACT_RELU);
+    Tensor t2 = ex.alloc(x.n, ho, wo, planes);
+    ex.conv(p + ".conv2", t1, t2, stride, 1, FCP_ACT_RELU);
+    ex.free(t1);
+    Tensor sc = x;
+    if (down) {
+        sc = ex.alloc(x.n, ho, wo, planes * 4);
+        ex.conv(p + ".downsample", x, sc, stride, 0, FCP_ACT_NONE);
+    }
+    Tensor out = ex.alloc(x.n, ho, wo, planes * 4);
+    ex.conv(p + ".conv3", t2, out, 1, 0, FCP_ACT_RELU, with_res1(sc));
+    ex.free(t2);
+    if (down) ex.free(sc);
+    return out;
+}
+
+// SSH context module (_layers.py:90-97); the final relu(cat(...)) is distributed into the three producing epilogues
+static Tensor ssh(Exec& ex, const std::string& p, Tensor x) {
+    Tensor out = ex.alloc(x.n, x.h, x.w, 256);
+    ex.conv(p + ".conv3X3", x, out.slice(0, 128), 1, 1, FCP_ACT_RELU);
+    Tensor c51 = ex.alloc(x.n, x.h, x.w, 64);
+    ex.conv(p + ".conv5X5_1", x, c51, 1, 1, FCP_ACT_RELU);
+    ex.conv(p + ".conv5X5_2", c51, out.slice(128, 64), 1, 1, FCP_ACT_RELU);
+    Tensor c72 = ex.alloc(x.n, x.h, x.w, 64);
+    ex.conv(p + ".conv7X7_2", c51, c72, 1, 1, FCP_ACT_RELU);
+    ex.free(c51);
+    ex.conv(p + ".conv7x7_3", c72, out.slice(192, 64), 1, 1, FCP_ACT_RELU);
+    ex.free(c72);
+    return out;
+}
+
+// RetinaFace.forward up to the raw head outputs (retinaface.py:112-142); lvl[i] = [nb, fh_i, fw_i, 32]
+static int retinaface_forward(Exec& ex, const uint8_t* images, int nb, int h, int w, Tensor lvl[3]) {
+    const ConvWeights* stem = ex.W("body.conv1");
+    if (!stem) return ex.status;
+    Tensor s1 = ex.alloc(nb, odim(h, 7, 2, 3), odim(w, 7, 2, 3), 64);
+    if (ex.ok() && !ex.dry) ex.status = launch_stem7(ex.ctx, images, 0, nb, h, w, stem->w_kn, stem->scale, stem->shift, s1);
+    Tensor x = ex.alloc(nb, odim(s1.h, 3, 2, 1), odim(s1.w, 3, 2, 1), 64);
+    if (ex.ok() && !ex.dry) ex.status = launch_maxpool3s2(ex.ctx, s1, x);
+    ex.free(s1);
+    const int blocks[4] = {3, 4, 6, 3}, planes[4] = {64, 128, 256, 512};
+    Tensor feats[3];
+    for (int li = 1; li <= 4; ++li) {
+        for (int b = 0; b < blocks[li - 1]; ++b) {
+            Tensor y = bottleneck(ex, "body.layer" + std::to_string(li) + "." + std::to_string(b), x, planes[li - 1],
+                                  (b == 0 && li > 1) ? 2 : 1, b == 0);
+            // the input of layer3.0 / layer4.0 is C3 / C4, still needed by the FPN; every other block input dies here
+            bool x_is_feat = (li >= 3 && b == 0);
+            if (!x_is_feat) ex.free(x);
+            x = y;
+        }
+        if (li >= 2) feats[li - 2] = x;
+    }
+    // FPN (_layers.py:127-145): 1x1 lateral convs, top-down nearest upsample + add, 3x3 merge convs
+    Tensor o3 = ex.alloc(nb, feats[2].h, feats[2].w, 256);
+    ex.conv("fpn.output3", feats[2], o3, 1, 0, FCP_ACT_RELU);
+    ex.free(feats[2]);
+    Tensor o2 = ex.alloc(nb, feats[1].h, feats[1].w, 256);
+    {
+        ConvOp e;
+        e.res2 = o3.p; e.res2_cs = o3.cs; e.res2_co = o3.co; e.res2_h = o3.h; e.res2_w = o3.w;
+        ex.conv("fpn.output2", feats[1], o2, 1, 0, FCP_ACT_RELU, e);
+    }
+    ex.free(feats[1]);
+    Tensor m2 = ex.alloc(nb, o2.h, o2.w, 256);
+    ex.conv("fpn.merge2", o2, m2, 1, 1, FCP_ACT_RELU);
+    ex.free(o2);
+    Tensor o1 = ex.alloc(nb, feats[0].h, feats[0].w, 256);
+    {
+        ConvOp e;
+        e.res2 = m2.p; e.res2_cs = m2.cs; e.res2_co = m2.co; e.res2_h = m2.h; e.res2_w = m2.w;
+        ex.conv("fpn.output1", feats[0], o1, 1, 0, FCP_ACT_RELU, e);
+    }
+    ex.free(feats[0]);
+    Tensor m1 = ex.alloc(nb, o1.h, o1.w, 256);
+    ex.conv("fpn.merge1", o1, m1, 1, 1, FCP_ACT_RELU);
+    ex.free(o1);
+    Tensor fpn[3] = {m1, m2, o3};
+    for (int i = 0; i < 3; ++i) {
+        Tensor f = ssh(ex, "ssh" + std::to_string(i + 1), fpn[i]);
+        ex.free(fpn[i]);
+        lvl[i] = ex.alloc(nb, f.h, f.w, 32);
+        ex.conv("heads." + std::to_string(i), f, lvl[i], 1, 0, FCP_ACT_NONE);
+        ex.free(f);
+    }
+    return ex.status;
+}
+
+// ============================================================================================== BiSeNet graph
+int finalize_bisenet(fcp_ctx* ctx) {
+    Model& m = ctx->models[FCP_MODEL_BISENET];
+    FCP_TRY(pack_conv(ctx, m, {"cp.resnet.conv1"}, "cp.resnet.bn1", "cp.resnet.conv1"));
+    for (int li = 1; li <= 4; ++li)
+        for (int b = 0; b < 2; ++b) {
+            std::string p = "cp.resnet.layer" + std::to_string(li) + "." + std::to_string(b);
+            FCP_TRY(pack_conv(ctx, m, {p + ".conv1"}, p + ".bn1", p + ".conv1"));
+            FCP_TRY(pack_conv(ctx, m, {p + ".conv2"}, p + ".bn2", p + ".conv2"));
+            if (b == 0 && li > 1) FCP_TRY(pack_conv(ctx, m, {p + ".downsample.0"}, p + ".downsample.1", p + ".downsample"));
+        }
+    for (const char* a : {"cp.arm16", "cp.arm32"}) {
+        FCP_TRY(pack_conv(ctx, m, {std::string(a) + ".conv.conv"}, std::string(a) + ".conv.bn", std::string(a) + ".conv"));
+        FCP_TRY(pack_conv(ctx, m, {std::string(a) + ".conv_atten"}, std::string(a) + ".bn_atten", std::string(a) + ".atten"));
+    }
+    for (const char* c : {"cp.conv_head32", "cp.conv_head16", "cp.conv_avg", "ffm.convblk", "conv_out.conv"})
+        FCP_TRY(pack_conv(ctx, m, {std::string(c) + ".conv"}, std::string(c) + ".bn", c));
+    FCP_TRY(pack_conv(ctx, m, {"ffm.conv1"}, "", "ffm.conv1"));
+    FCP_TRY(pack_conv(ctx, m, {"ffm.conv2"}, "", "ffm.conv2"));
+    FCP_TRY(pack_conv(ctx, m, {"conv_out.conv_out"}, "", "conv_out.conv_out"));
+    return FCP_OK;
+}
+
+// BasicBlock (_layers.py:226-239)
+static Tensor basic_block(Exec& ex, const std::string& p, Tensor x, int cout, int stride, bool down, Tensor* out_view) {
+    int ho = odim(x.h, 3, stride, 1), wo = odim(x.w, 3, stride, 1);
+    Tensor t = ex.alloc(x.n, ho, wo, cout);
+    ex.conv(p + ".conv1", x, t, stride, 1, FCP_ACT_RELU);
+    Tensor sc = x;
+    if (down) {
+        sc = ex.alloc(x.n, ho, wo, cout);
+        ex.conv(p + ".downsample", x, sc, stride, 0, FCP_ACT_NONE);
+    }
+    Tensor out = out_view ? *out_view : ex.alloc(x.n, ho, wo, cout);
+    ex.conv(p + ".conv2", t, out, 1, 1, FCP_ACT_RELU, with_res1(sc));
+    ex.free(t);
+    if (down) ex.free(sc);
+    return out;
+}
+
+// AttentionRefinementModule (_layers.py:305-313) followed by "+ addvec" (ContextPath, _layers.py:336)
+static Tensor arm(Exec& ex, const std::string& p, Tensor x, const float* addvec) {
+    Tensor feat = ex.alloc(x.n, x.h, x.w, 128);
+    ex.conv(p + ".conv", x, feat, 1, 1, FCP_ACT_RELU);
+    float* pooled = ex.alloc_vec((size_t)x.n * 128);
+    float* att = ex.alloc_vec((size_t)x.n * 128);
+    const ConvWeights* wa = ex.W(p + ".atten");
+    if (ex.ok() && !ex.dry) ex.status = launch_global_avgpool(ex.ctx, feat, pooled);
+    if (ex.ok() && !ex.dry) ex.status = launch_fc(ex.ctx, pooled, x.n, 128, wa, FCP_ACT_SIGMOID, att);
+    Tensor out = ex.alloc(x.n, x.h, x.w, 128);
+    if (ex.ok() && !ex.dry) ex.status = launch_channel_affine(ex.ctx, feat, att, addvec, 0, out);
+    ex.free(feat);
+    ex.free_vec(pooled);
+    ex.free_vec(att);
+    return out;
+}
+
+// BiSeNet.forward up to conv_out (bise.py:211; _layers.py:326-368); logits = [nb, 64, 64, 19] with channel stride 32
+static int bisenet_forward(Exec& ex, const float* in3, int nb, Tensor& logits) {
+    const ConvWeights* stem = ex.W("cp.resnet.conv1");
+    if (!stem) return ex.status;
+    Tensor s1 = ex.alloc(nb, 256, 256, 64);
+    if (ex.ok() && !ex.dry) ex.status = launch_stem7(ex.ctx, in3, 1, nb, 512, 512, stem->w_kn, stem->scale, stem->shift, s1);
+    Tensor x = ex.alloc(nb, 128, 128, 64);
+    if (ex.ok() && !ex.dry) ex.status = launch_maxpool3s2(ex.ctx, s1, x);
+    ex.free(s1);
+    // the FFM concat buffer: [feat8 | feat16_up] (_layers.py:358)
+    Tensor cat = ex.alloc(nb, 64, 64, 256);
+    Tensor feat8v = cat.slice(0, 128), feat16upv = cat.slice(128, 128);
+    const int couts[4] = {64, 128, 256, 512};
+    Tensor feat16, feat32;
+    for (int li = 1; li <= 4; ++li) {
+        std::string p = "cp.resnet.layer" + std::to_string(li);
+        Tensor y = basic_block(ex, p + ".0", x, couts[li - 1], li > 1 ? 2 : 1, li > 1, nullptr);
+        if (li != 3 && li != 4) ex.free(x);          // feat8 lives in `cat`; feat16 is freed later
+        else if (li == 3) { /* x == feat8 view inside cat: keep */ }
+        Tensor z = basic_block(ex, p + ".1", y, couts[li - 1], 1, false, li == 2 ? &feat8v : nullptr);
+        ex.free(y);
+        x = z;
+        if (li == 3) feat16 = z;
+        if (li == 4) feat32 = z;
+    }
+    // ContextPath (_layers.py:326-346)
+    float* pooled = ex.alloc_vec((size_t)nb * 512);
+    float* avgv = ex.alloc_vec((size_t)nb * 128);
+    if (ex.ok() && !ex.dry) ex.status = launch_global_avgpool(ex.ctx, feat32, pooled);
+    if (ex.ok() && !ex.dry) ex.status = launch_fc(ex.ctx, pooled, nb, 512, ex.W("cp.conv_avg"), FCP_ACT_RELU, avgv);
+    Tensor feat32_sum = arm(ex, "cp.arm32", feat32, avgv);          // arm32(feat32) + avg_up (broadcast of a 1x1 map)
+    ex.free(feat32);
+    ex.free_vec(pooled);
+    Tensor feat16_arm = arm(ex, "cp.arm16", feat16, nullptr);
+    ex.free(feat16);
+    Tensor feat16_sum = ex.alloc(nb, 32, 32, 128);
+    {
+        ConvOp e;                                                   // conv_head32(up(feat32_sum)) + feat16_arm
+        e.up_in = 1;
+        e.res2 = feat16_arm.p; e.res2_cs = feat16_arm.cs; e.res2_co = feat16_arm.co;
+        ex.conv("cp.conv_head32", feat32_sum, feat16_sum, 1, 1, FCP_ACT_RELU, e);
+    }
+    ex.free(feat32_sum);
+    ex.free(feat16_arm);
+    ex.free_vec(avgv);
+    {
+        ConvOp e;
+        e.up_in = 1;
+        ex.conv("cp.conv_head16", feat16_sum, feat16upv, 1, 1, FCP_ACT_RELU, e);
+    }
+    ex.free(feat16_sum);
+    // FeatureFusionModule (_layers.py:357-368)
+    Tensor feat = ex.alloc(nb, 64, 64, 256);
+    ex.conv("ffm.convblk", cat, feat, 1, 0, FCP_ACT_RELU);
+    ex.free(cat);
+    float* p1 = ex.alloc_vec((size_t)nb * 256);
+    float* p2 = ex.alloc_vec((size_t)nb * 64);
+    float* p3 = ex.alloc_vec((size_t)nb * 256);
+    if (ex.ok() && !ex.dry) ex.status = launch_global_avgpool(ex.ctx, feat, p1);
+    if (ex.ok() && !ex.dry) ex.status = launch_fc(ex.ctx, p1, nb, 256, ex.W("ffm.conv1"), FCP_ACT_RELU, p2);
+    if (ex.ok() && !ex.dry) ex.status = launch_fc(ex.ctx, p2, nb, 64, ex.W("ffm.conv2"), FCP_ACT_SIGMOID, p3);
+    Tensor fused = ex.alloc(nb, 64, 64, 256);
+    if (ex.ok() && !ex.dry) ex.status = launch_channel_affine(ex.ctx, feat, p3, nullptr, 1, fused);   // feat*att + feat
+    ex.free(feat);
+    ex.free_vec(p1); ex.free_vec(p2); ex.free_vec(p3);
+    // BiSeNetOutput (_layers.py:291-295)
+    Tensor mid = ex.alloc(nb, 64, 64, 256);
+    ex.conv("conv_out.conv", fused, mid, 1, 1, FCP_ACT_RELU);
+    ex.free(fused);
+    logits = ex.alloc(nb, 64, 64, 19, 32);
+    ex.conv("conv_out.conv_out", mid, logits, 1, 0, FCP_ACT_NONE);
+    ex.free(mid);
+    return ex.status;
+}
+
+// ============================================================================================== RRDBNet graph
+int finalize_rrdbnet(fcp_ctx* ctx) {
+    Model& m = ctx->models[FCP_MODEL_RRDBNET];
+    FCP_TRY(pack_conv(ctx, m, {"conv_first"}, "", "conv_first"));
+    for (int i = 0; i < m.rrdb_blocks; ++i)
+        for (int r = 1; r <= 3; ++r)
+            for (int c = 1; c <= 5; ++c) {
+                std::string p = "RRDB_trunk." + std::to_string(i) + ".RDB" + std::to_string(r) + ".conv" + std::to_string(c);
+                FCP_TRY(pack_conv(ctx, m, {p}, "", p));
+            }
+    for (const char* c : {"trunk_conv", "upconv1", "upconv2", "HRconv", "conv_last"}) FCP_TRY(pack_conv(ctx, m, {c}, "", c));
+    return FCP_OK;
+}
+
+// RRDBNet.forward (rrdb.py:64-81) on nb images [nb,3,h,w] NCHW scaled by 1/in_div; result x4 = [nb,4h,4w,3] (cs 4)
+static int rrdbnet_forward(Exec& ex, const float* x_nchw, float in_div, int nb, int h, int w, Tensor& x4) {
+    const ConvWeights* cf = ex.W("conv_first");
+    if (!cf) return ex.status;
+    Tensor first = ex.alloc(nb, h, w, 64);
+    if (ex.ok() && !ex.dry) ex.status = launch_conv3_first(ex.ctx, x_nchw, in_div, nb, h, w, cf->w_kn, cf->shift, first);
+    // three rotating 192-channel slabs [x | x1 | x2 | x3 | x4]: the dense concatenations of
+    // ResidualDenseBlock_5C (_layers.py:179-186) are channel-prefix views of one slab
+    Tensor slab[3];
+    for (auto& s : slab) s = ex.alloc(nb, h, w, 192);
+    if (ex.ok() && !ex.dry)
+        ex.status = cudaMemcpy2DAsync(slab[0].p, 192 * sizeof(float), first.p, 64 * sizeof(float), 64 * sizeof(float),
+                                      first.pixels(), cudaMemcpyDeviceToDevice, ex.ctx->stream) == cudaSuccess
+                        ? FCP_OK : fail(ex.ctx, FCP_ERR_CUDA, "slab init copy failed");
+    int cur = 0;
+    for (int i = 0; i < ex.model->rrdb_blocks && ex.ok(); ++i) {
+        const int order_in[3] = {cur, (cur + 1) % 3, (cur + 2) % 3};
+        const int order_out[3] = {(cur + 1) % 3, (cur + 2) % 3, (cur + 1) % 3};
+        for (int r = 0; r < 3; ++r) {
+            std::string p = "RRDB_trunk." + std::to_string(i) + ".RDB" + std::to_string(r + 1);
+            Tensor S = slab[order_in[r]], T = slab[order_out[r]];
+            ConvOp lre;
+            lre.slope = 0.2f;
+            for (int c = 1; c <= 4; ++c)
+                ex.conv(p + ".conv" + std::to_string(c), S.slice(0, 64 + 32 * (c - 1)), S.slice(32 + 32 * c, 32), 1, 1,
+                        FCP_ACT_LRELU, lre);
+            ConvOp e;                                   // x5 * 0.2 + x   (_layers.py:186)
+            e.post_scale = 0.2f;
+            e.res2 = S.p; e.res2_cs = S.cs; e.res2_co = 0;
+            if (r == 2) {                               // RRDB: out * 0.2 + x   (_layers.py:200)
+                e.post_scale2 = 0.2f;
+                e.res3 = slab[cur].p; e.res3_cs = 192; e.res3_co = 0;
+            }
+            ex.conv(p + ".conv5", S, T.slice(0, 64), 1, 1, FCP_ACT_NONE, e);
+        }
+        cur = (cur + 1) % 3;
+    }
+    Tensor fea = ex.alloc(nb, h, w, 64);
+    ex.conv("trunk_conv", slab[cur].slice(0, 64), fea, 1, 1, FCP_ACT_NONE, with_res1(first));   // first + trunk_conv(..)
+    for (auto& s : slab) ex.free(s);
+    ex.free(first);
+    ConvOp up;
+    up.up_in = 1; up.slope = 0.2f;
+    Tensor u1 = ex.alloc(nb, 2 * h, 2 * w, 64);
+    ex.conv("upconv1", fea, u1, 1, 1, FCP_ACT_LRELU, up);
+    ex.free(fea);
+    Tensor u2 = ex.alloc(nb, 4 * h, 4 * w, 64);
+    ex.conv("upconv2", u1, u2, 1, 1, FCP_ACT_LRELU, up);
+    ex.free(u1);
+    ConvOp lre;
+    lre.slope = 0.2f;
+    Tensor hr = ex.alloc(nb, 4 * h, 4 * w, 64);
+    ex.conv("HRconv", u2, hr, 1, 1, FCP_ACT_LRELU, lre);
+    ex.free(u2);
+    x4 = ex.alloc(nb, 4 * h, 4 * w, 3, 4);
+    ex.conv("conv_last", hr, x4, 1, 1, FCP_ACT_NONE);
+    ex.free(hr);
+    return ex.status;
+}
+
+// ------------------------------------------------------------------------------------------ plan + reserve
+static int plan_reserve(fcp_ctx* ctx, Model* model, const std::vector<std::function<int(Exec&)>>& graphs) {
+    size_t need = 0;
+    for (auto& g : graphs) {
+        ctx->arena.set_plan_mode(true);
+        Exec ex{ctx, model, true};
+        int s = g(ex);
+        size_t hw = ctx->arena.high_water();
+        ctx->arena.set_plan_mode(false);
+        if (s != FCP_OK) return s;
+        need = std::max(need, hw);
+    }
+    if (!ctx->arena.reserve(std::max(need, ctx->arena.capacity())))
+        return fail(ctx, FCP_ERR_CUDA, "cannot reserve activation arena of " + std::to_string(need >> 20) + " MiB");
+    ctx->arena.reset();
+    return FCP_OK;
+}
+
+static int need_model(fcp_ctx* ctx, int model) {
+    if (!ctx) return FCP_ERR_INVALID;
+    if (!ctx->models[model].finalized) return fail(ctx, FCP_ERR_STATE, "model weights not finalized (fcp_load_tensor + fcp_finalize)");
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, FCP_ERR_CUDA, "cudaSetDevice failed");
+    return FCP_OK;
+}
+
+// ============================================================================================== detect core
+// Runs the detector over micro-batches; faces (device) receives up to max_faces 16-float records in image order.
+static int detect_core(fcp_ctx* ctx, const uint8_t* images, int n, int h, int w, float vis, float nms, int strategy,
+                       int max_faces, float* faces, int32_t* face_img, int32_t* face_count, float* heads_out) {
+    Model* model = &ctx->models[FCP_MODEL_RETINAFACE];
+    const int mb = std::min(ctx->det_mb, n);
+    std::vector<std::function<int(Exec&)>> plans;
+    for (int nb : {mb, n % mb})
+        if (nb > 0) plans.push_back([=](Exec& ex) { Tensor l[3]; return retinaface_forward(ex, nullptr, nb, h, w, l); });
+    FCP_TRY(plan_reserve(ctx, model, plans));
+    const int A = det_num_priors(h, w), key_cap = det_key_capacity(h, w);
+    float* rec = nullptr; unsigned long long* keys = nullptr; unsigned char* supp = nullptr; int32_t* counts = nullptr;
+    if (!heads_out) {
+        FCP_CUDA(ctx, cudaMallocAsync(&rec, (size_t)mb * A * 16 * sizeof(float), ctx->stream));
+        FCP_CUDA(ctx, cudaMallocAsync(&keys, (size_t)mb * key_cap * sizeof(unsigned long long), ctx->stream));
+        FCP_CUDA(ctx, cudaMallocAsync(&supp, (size_t)mb * key_cap, ctx->stream));
+        FCP_CUDA(ctx, cudaMallocAsync(&counts, sizeof(int32_t) * 2 * mb, ctx->stream));
+        FCP_CUDA(ctx, cudaMemsetAsync(face_count, 0, sizeof(int32_t), ctx->stream));
+    }
+    int status = FCP_OK;
+    for (int b0 = 0; b0 < n && status == FCP_OK; b0 += mb) {
+        int nb = std::min(mb, n - b0);
+        ctx->arena.reset();
+        Exec ex{ctx, model, false};
+        Tensor lvl[3];
+        status = retinaface_forward(ex, images + (size_t)b0 * h * w * 3, nb, h, w, lvl);
+        if (status != FCP_OK) break;
+        const float* ptrs[3] = {lvl[0].p, lvl[1].p, lvl[2].p};
+        if (heads_out) status = launch_heads_to_flat(ctx, ptrs, nb, h, w, heads_out + (size_t)b0 * A * 16);
+        else status = launch_det_post(ctx, ptrs, nullptr, nb, b0, h, w, vis, nms, strategy, max_faces, rec, keys, supp,
+                                      counts, counts + mb, faces, face_img, face_count);
+    }
+    if (rec) cudaFreeAsync(rec, ctx->stream);
+    if (keys) cudaFreeAsync(keys, ctx->stream);
+    if (supp) cudaFreeAsync(supp, ctx->stream);
+    if (counts) cudaFreeAsync(counts, ctx->stream);
+    return status;
+}
+
+// =============================================================================================== parse core
+static int parse_core(fcp_ctx* ctx, const uint8_t* crops, int f, int h, int w, uint8_t* labels, int32_t* hist,
+                      float* logits_nchw) {
+    if (f == 0) return FCP_OK;
+    Model* model = &ctx->models[FCP_MODEL_BISENET];
+    const int mb = std::min(ctx->par_mb, f);
+    auto graph = [=](Exec& ex, const uint8_t* src, int nb, Tensor& logits) -> int {
+        Tensor in3 = ex.alloc(nb, 512, 512, 3, 3);
+        if (ex.ok() && !ex.dry) ex.status = launch_parse_prep(ctx, src, nb, h, w, in3.p);
+        bisenet_forward(ex, in3.p, nb, logits);
+        ex.free(in3);
+        return ex.status;
+    };
+    std::vector<std::function<int(Exec&)>> plans;
+    for (int nb : {mb, f % mb})
+        if (nb > 0) plans.push_back([=](Exec& ex) { Tensor l; return graph(ex, nullptr, nb, l); });
+    FCP_TRY(plan_reserve(ctx, model, plans));
+    for (int b0 = 0; b0 < f; b0 += mb) {
+        int nb = std::min(mb, f - b0);
+        ctx->arena.reset();
+        Exec ex{ctx, model, false};
+        Tensor logits;
+        FCP_TRY(graph(ex, crops + (size_t)b0 * h * w * 3, nb, logits));
+        if (logits_nchw)
+            FCP_TRY(launch_nhwc_to_nchw(ctx, logits.p, nb, 64, 64, 19, logits.cs, logits_nchw + (size_t)b0 * 19 * 64 * 64));
+        if (labels || hist)
+            FCP_TRY(launch_parse_tail(ctx, logits.p, 1, logits.cs, nb, 64, 64, h, w, labels ? labels + (size_t)b0 * h * w : nullptr,
+                                      hist ? hist + (size_t)b0 * 19 : nullptr));
+    }
+    return FCP_OK;
+}
+
+// =============================================================================================== align core
+static int align_core(fcp_ctx* ctx, const uint8_t* images, int n, int h, int w, const uint8_t* const* ptrs,
+                      const int32_t* hs, const int32_t* ws, const int32_t* paddings, const int32_t* indices,
+                      const int32_t* face_count_dev, const float* landmarks, int f, const float* target, int out_w,
+                      int out_h, int border, int skew, uint8_t* crops, double* matrices, uint8_t* valid) {
+    if (f == 0) return FCP_OK;
+    double* inv = nullptr;
+    FCP_CUDA(ctx, cudaMallocAsync(&inv, sizeof(double) * 6 * f, ctx->stream));
+    int s = launch_solve(ctx, landmarks, face_count_dev, f, target, skew, matrices, inv, valid);
+    if (s == FCP_OK)
+        s = launch_warp(ctx, images, n, h, w, ptrs, hs, ws, paddings, indices, face_count_dev, f, inv, valid, out_w, out_h, border, crops);
+    cudaFreeAsync(inv, ctx->stream);
+    return s;
+}
+
+}  // namespace fcp
+
+// ======================================================================================================= C ABI
+using namespace fcp;
+
+extern "C" {
+
+static int detect_outputs(fcp_ctx* ctx, const float* faces, const int32_t* face_img, const int32_t* face_count, int max_faces,
+                          float* out_landmarks, int32_t* out_indices, float* out_boxes, float* out_scores,
+                          int32_t* out_anchors, int32_t* out_count) {
+    DevOut lms, idx, box, sc, an;
+    FCP_TRY(lms.init(ctx, out_landmarks, sizeof(float) * 10 * max_faces));
+    FCP_TRY(box.init(ctx, out_boxes, sizeof(float) * 4 * max_faces));
+    FCP_TRY(sc.init(ctx, out_scores, sizeof(float) * max_faces));
+    FCP_TRY(an.init(ctx, out_anchors, sizeof(int32_t) * max_faces));
+    FCP_TRY(launch_unpack_faces(ctx, faces, face_img, face_count, max_faces, nullptr, lms.as<float>(), box.as<float>(),
+                                sc.as<float>(), an.as<int32_t>()));
+    int32_t count = 0;
+    FCP_CUDA(ctx, cudaMemcpyAsync(&count, face_count, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    FCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int got = std::min(count, max_faces);
+    FCP_TRY(lms.flush(sizeof(float) * 10 * got));
+    FCP_TRY(box.flush(sizeof(float) * 4 * got));
+    FCP_TRY(sc.flush(sizeof(float) * got));
+    FCP_TRY(an.flush(sizeof(int32_t) * got));
+    if (out_indices && got) {
+        FCP_CUDA(ctx, cudaMemcpyAsync(out_indices, face_img, sizeof(int32_t) * got,
+                                      is_device_ptr(out_indices) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (is_device_ptr(out_count)) FCP_CUDA(ctx, cudaMemcpyAsync(out_count, &count, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    else *out_count = count;
+    FCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (count > max_faces) return fail(ctx, FCP_ERR_CAPACITY, "max_faces too small: " + std::to_string(count) + " faces found");
+    return FCP_OK;
+}
+
+int fcp_detect(fcp_ctx* ctx, const uint8_t* images, int n, int h, int w, float vis_threshold, float nms_threshold,
+               int strategy, int max_faces, float* out_landmarks, int32_t* out_indices, float* out_boxes,
+               float* out_scores, int32_t* out_anchors, int32_t* out_count) {
+    FCP_TRY(need_model(ctx, FCP_MODEL_RETINAFACE));
+    if (!images || n < 1 || h < 32 || w < 32 || max_faces < 1 || !out_count || strategy < 0 || strategy > 2)
+        return fail(ctx, FCP_ERR_INVALID, "fcp_detect: bad argument");
+    DevIn img;
+    FCP_TRY(img.init(ctx, images, (size_t)n * h * w * 3));
+    float* faces; int32_t* face_img; int32_t* face_count;
+    FCP_CUDA(ctx, cudaMallocAsync(&faces, sizeof(float) * 16 * max_faces, ctx->stream));
+    FCP_CUDA(ctx, cudaMallocAsync(&face_img, sizeof(int32_t) * max_faces, ctx->stream));
+    FCP_CUDA(ctx, cudaMallocAsync(&face_count, sizeof(int32_t), ctx->stream));
+    int s = detect_core(ctx, img.as<uint8_t>(), n, h, w, vis_threshold, nms_threshold, strategy, max_faces, faces, face_img,
+                        face_count, nullptr);
+    if (s == FCP_OK)
+        s = detect_outputs(ctx, faces, face_img, face_count, max_faces, out_landmarks, out_indices, out_boxes, out_scores,
+                           out_anchors, out_count);
+    cudaFreeAsync(faces, ctx->stream); cudaFreeAsync(face_img, ctx->stream); cudaFreeAsync(face_count, ctx->stream);
+    return s;
+}
+
+int fcp_detect_heads(fcp_ctx* ctx, const uint8_t* images, int n, int h, int w, float* out_heads) {
+    FCP_TRY(need_model(ctx, FCP_MODEL_RETINAFACE));
+    if (!images || !out_heads || n < 1 || h < 32 || w < 32) return fail(ctx, FCP_ERR_INVALID, "fcp_detect_heads: bad argument");
+    DevIn img;
+    FCP_TRY(img.init(ctx, images, (size_t)n * h * w * 3));
+    DevOut heads;
+    FCP_TRY(heads.init(ctx, out_heads, sizeof(float) * 16 * (size_t)det_num_priors(h, w) * n));
+    FCP_TRY(detect_core(ctx, img.as<uint8_t>(), n, h, w, 0, 0, 0, 0, nullptr, nullptr, nullptr, heads.as<float>()));
+    FCP_TRY(heads.flush());
+    FCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FCP_OK;
+}
+
+int fcp_detect_post(fcp_ctx* ctx, const float* heads, int n, int h, int w, float vis_threshold, float nms_threshold,
+                    int strategy, int max_faces, float* out_landmarks, int32_t* out_indices, float* out_boxes,
+                    float* out_scores, int32_t* out_anchors, int32_t* out_count) {
+    if (!ctx || !heads || n < 1 || max_faces < 1 || !out_count || strategy < 0 || strategy > 2)
+        return fail(ctx, FCP_ERR_INVALID, "fcp_detect_post: bad argument");
+    FCP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int A = det_num_priors(h, w), key_cap = det_key_capacity(h, w);
+    DevIn hd;
+    FCP_TRY(hd.init(ctx, heads, sizeof(float) * 16 * (size_t)A * n));
+    float *rec, *faces; unsigned long long* keys; unsigned char* supp; int32_t *counts, *face_img, *face_count;
+    FCP_CUDA(ctx, cudaMallocAsync(&rec, (size_t)n * A * 16 * sizeof(float), ctx->stream));
+    FCP_CUDA(ctx, cudaMallocAsync(&keys, (size_t)n * key_cap * sizeof(unsigned long long), ctx->stream));
+    FCP_CUDA(ctx, cudaMallocAsync(&supp, (size_t)n * key_cap, ctx->stream));
+    FCP_CUDA(ctx, cudaMallocAsync(&counts, sizeof(int32_t) * 2 * n, ctx->stream));
+    FCP_CUDA(ctx, cudaMallocAsync(&faces, sizeof(float) * 16 * max_faces, ctx->stream));
+    FCP_CUDA(ctx, cudaMallocAsync(&face_img, sizeof(int32_t) * max_faces, ctx->stream));
+    FCP_CUDA(ctx, cudaMallocAsync(&face_count, sizeof(int32_t), ctx->stream));
+    FCP_CUDA(ctx, cudaMemsetAsync(face_count, 0, sizeof(int32_t), ctx->stream));
+    int s = launch_det_post(ctx, nullptr, hd.as<float>(), n, 0, h, w, vis_threshold, nms_threshold, strategy, max_faces, rec,
+                            keys, supp, counts, counts + n, faces, face_img, face_count);
+    if (s == FCP_OK)
+        s = detect_outputs(ctx, faces, face_img, face_count, max_faces, out_landmarks, out_indices, out_boxes, out_scores,
+                           out_anchors, out_count);
+    for (void* p : {(void*)rec, (void*)keys, (void*)supp, (void*)counts, (void*)faces, (void*)face_img, (void*)face_count})
+        cudaFreeAsync(p, ctx->stream);
+    return s;
+}
+
+static int align_api(fcp_ctx* ctx, const uint8_t* images, int n, int h, int w, const uint8_t* const* image_ptrs,
+                     const int32_t* hs, const int32_t* ws, const int32_t* paddings, const int32_t* indices,
+                     const float* landmarks, int f, const float* target, int out_w, int out_h, int border_mode,
+                     int allow_skew, uint8_t* out_crops, double* out_matrices, uint8_t* out_valid) {
+    if (!ctx || n < 0 || f < 0 || !target || out_w < 1 || out_h < 1 || border_mode < 0 || border_mode > 4 || (f && (!indices || !landmarks || !out_crops)))
+        return fail(ctx, FCP_ERR_INVALID, "fcp_align: bad argument");
+    FCP_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (f == 0) return FCP_OK;
+    DevIn img, pad, idx, lms, tgt, dptrs, dhs, dws;
+    std::vector<DevIn> list_imgs(image_ptrs ? n : 0);
+    std::vector<const uint8_t*> dev_ptrs;
+    if (image_ptrs) {
+        for (int i = 0; i < n; ++i) {
+            FCP_TRY(list_imgs[i].init(ctx, image_ptrs[i], (size_t)hs[i] * ws[i] * 3));
+            dev_ptrs.push_back(list_imgs[i].as<uint8_t>());
+        }
+        FCP_TRY(dptrs.init(ctx, dev_ptrs.data(), sizeof(void*) * n));
+        FCP_TRY(dhs.init(ctx, hs, sizeof(int32_t) * n));
+        FCP_TRY(dws.init(ctx, ws, sizeof(int32_t) * n));
+    } else {
+        FCP_TRY(img.init(ctx, images, (size_t)n * h * w * 3));
+    }
+    FCP_TRY(pad.init(ctx, paddings, sizeof(int32_t) * 4 * n));
+    FCP_TRY(idx.init(ctx, indices, sizeof(int32_t) * f));
+    FCP_TRY(lms.init(ctx, landmarks, sizeof(float) * 10 * f));
+    FCP_TRY(tgt.init(ctx, target, sizeof(float) * 10));
+    DevOut crops, mats, valid;
+    FCP_TRY(crops.init(ctx, out_crops, (size_t)f * out_h * out_w * 3));
+    FCP_TRY(mats.init(ctx, out_matrices, sizeof(double) * 6 * f, true));
+    FCP_TRY(valid.init(ctx, out_valid, f, true));
+    FCP_TRY(align_core(ctx, img.as<uint8_t>(), n, h, w, dptrs.as<const uint8_t*>(), dhs.as<int32_t>(), dws.as<int32_t>(),
+                       pad.as<int32_t>(), idx.as<int32_t>(), nullptr, lms.as<float>(), f, tgt.as<float>(), out_w, out_h,
+                       border_mode, allow_skew, crops.as<uint8_t>(), mats.as<double>(), valid.as<uint8_t>()));
+    FCP_TRY(crops.flush()); FCP_TRY(mats.flush()); FCP_TRY(valid.flush());
+    FCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FCP_OK;
+}
+
+int fcp_align(fcp_ctx* ctx, const uint8_t* images, int n, int h, int w, const int32_t* paddings, const int32_t* indices,
+              const float* landmarks, int f, const float* target, int out_w, int out_h, int border_mode, int allow_skew,
+              uint8_t* out_crops, double* out_matrices, uint8_t* out_valid) {
+    if (f > 0 && !images) return fail(ctx, FCP_ERR_INVALID, "fcp_align: images is NULL");
+    return align_api(ctx, images, n, h, w, nullptr, nullptr, nullptr, paddings, indices, landmarks, f, target, out_w, out_h,
+                     border_mode, allow_skew, out_crops, out_matrices, out_valid);
+}
+
+int fcp_align_list(fcp_ctx* ctx, const uint8_t* const* image_ptrs, const int32_t* hs, const int32_t* ws, int n,
+                   const int32_t* paddings, const int32_t* indices, const float* landmarks, int f, const float* target,
+                   int out_w, int out_h, int border_mode, int allow_skew, uint8_t* out_crops, double* out_matrices,
+                   uint8_t* out_valid) {
+    if (f > 0 && (!image_ptrs || !hs || !ws)) return fail(ctx, FCP_ERR_INVALID, "fcp_align_list: NULL image list");
+    return align_api(ctx, nullptr, n, 0, 0, image_ptrs, hs, ws, paddings, indices, landmarks, f, target, out_w, out_h,
+                     border_mode, allow_skew, out_crops, out_matrices, out_valid);
+}
+
+int fcp_parse(fcp_ctx* ctx, const uint8_t* crops, int f, int h, int w, uint8_t* out_labels, int32_t* out_hist) {
+    FCP_TRY(need_model(ctx, FCP_MODEL_BISENET));
+    if (f < 0 || h < 1 || w < 1 || (f && !crops)) return fail(ctx, FCP_ERR_INVALID, "fcp_parse: bad argument");
+    if (f == 0) return FCP_OK;
+    DevIn c;
+    FCP_TRY(c.init(ctx, crops, (size_t)f * h * w * 3));
+    DevOut lab, hist;
+    FCP_TRY(lab.init(ctx, out_labels, (size_t)f * h * w));
+    FCP_TRY(hist.init(ctx, out_hist, sizeof(int32_t) * 19 * f));
+    FCP_TRY(parse_core(ctx, c.as<uint8_t>(), f, h, w, lab.as<uint8_t>(), hist.as<int32_t>(), nullptr));
+    FCP_TRY(lab.flush()); FCP_TRY(hist.flush());
+    FCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FCP_OK;
+}
+
+int fcp_parse_logits(fcp_ctx* ctx, const uint8_t* crops, int f, int h, int w, float* out_logits) {
+    FCP_TRY(need_model(ctx, FCP_MODEL_BISENET));
+    if (f < 1 || !crops || !out_logits) return fail(ctx, FCP_ERR_INVALID, "fcp_parse_logits: bad argument");
+    DevIn c;
+    FCP_TRY(c.init(ctx, crops, (size_t)f * h * w * 3));
+    DevOut lg;
+    FCP_TRY(lg.init(ctx, out_logits, sizeof(float) * 19 * 64 * 64 * f));
+    FCP_TRY(parse_core(ctx, c.as<uint8_t>(), f, h, w, nullptr, nullptr, lg.as<float>()));
+    FCP_TRY(lg.flush());
+    FCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FCP_OK;
+}
+
+int fcp_parse_tail(fcp_ctx* ctx, const float* logits, int f, int h, int w, uint8_t* out_labels, int32_t* out_hist) {
+    if (!ctx || f < 0 || (f && !logits)) return fail(ctx, FCP_ERR_INVALID, "fcp_parse_tail: bad argument");
+    FCP_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (f == 0) return FCP_OK;
+    DevIn lg;
+    FCP_TRY(lg.init(ctx, logits, sizeof(float) * 19 * 64 * 64 * f));
+    DevOut lab, hist;
+    FCP_TRY(lab.init(ctx, out_labels, (size_t)f * h * w));
+    FCP_TRY(hist.init(ctx, out_hist, sizeof(int32_t) * 19 * f));
+    FCP_TRY(launch_parse_tail(ctx, lg.as<float>(), 0, 0, f, 64, 64, h, w, lab.as<uint8_t>(), hist.as<int32_t>()));
+    FCP_TRY(lab.flush()); FCP_TRY(hist.flush());
+    FCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FCP_OK;
+}
+
+int fcp_masks(fcp_ctx* ctx, const uint8_t* labels, int f, int h, int w, const uint8_t* class_lut19, uint8_t* out_masks) {
+    if (!ctx || f < 0 || !class_lut19 || (f && (!labels || !out_masks))) return fail(ctx, FCP_ERR_INVALID, "fcp_masks: bad argument");
+    FCP_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (f == 0) return FCP_OK;
+    size_t count = (size_t)f * h * w;
+    DevIn lab, lut;
+    FCP_TRY(lab.init(ctx, labels, count));
+    FCP_TRY(lut.init(ctx, class_lut19, 19));
+    DevOut out;
+    FCP_TRY(out.init(ctx, out_masks, count));
+    FCP_TRY(launch_masks(ctx, lab.as<uint8_t>(), count, lut.as<uint8_t>(), out.as<uint8_t>()));
+    FCP_TRY(out.flush());
+    FCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FCP_OK;
+}
+
+static int enhance_core(fcp_ctx* ctx, const float* x, float in_div, int n, int h, int w, const uint8_t* gate_host,
+                        float* out_x4_nchw, float* out_x1_nchw) {
+    Model* model = &ctx->models[FCP_MODEL_RRDBNET];
+    std::vector<std::function<int(Exec&)>> plans;
+    plans.push_back([=](Exec& ex) { Tensor t; return rrdbnet_forward(ex, nullptr, in_div, 1, h, w, t); });
+    FCP_TRY(plan_reserve(ctx, model, plans));
+    for (int i = 0; i < n; ++i) {                       // one image at a time, like rrdb.py:124-144
+        if (gate_host && !gate_host[i]) continue;
+        ctx->arena.reset();
+        Exec ex{ctx, model, false};
+        Tensor x4;
+        FCP_TRY(rrdbnet_forward(ex, x + (size_t)i * 3 * h * w, in_div, 1, h, w, x4));
+        if (out_x4_nchw) FCP_TRY(launch_nhwc_to_nchw(ctx, x4.p, 1, 4 * h, 4 * w, 3, x4.cs, out_x4_nchw + (size_t)i * 3 * 16 * h * w));
+        if (out_x1_nchw) FCP_TRY(launch_rrdb_tail(ctx, x4, out_x1_nchw + (size_t)i * 3 * h * w, h, w));
+    }
+    return FCP_OK;
+}
+
+int fcp_enhance(fcp_ctx* ctx, float* images, int n, int h, int w, const uint8_t* do_enhance) {
+    FCP_TRY(need_model(ctx, FCP_MODEL_RRDBNET));
+    if (!images || n < 1 || h < 1 || w < 1) return fail(ctx, FCP_ERR_INVALID, "fcp_enhance: bad argument");
+    size_t bytes = sizeof(float) * 3 * h * w * (size_t)n;
+    std::vector<uint8_t> gate(n, 1);
+    if (do_enhance) {
+        if (is_device_ptr(do_enhance)) FCP_CUDA(ctx, cudaMemcpy(gate.data(), do_enhance, n, cudaMemcpyDeviceToHost));
+        else gate.assign(do_enhance, do_enhance + n);
+    }
+    if (is_device_ptr(images)) {
+        // in-place on device: the tail writes image i only after the whole graph of image i has consumed it
+        FCP_TRY(enhance_core(ctx, images, 255.f, n, h, w, gate.data(), nullptr, images));
+    } else {
+        float* dev;
+        FCP_CUDA(ctx, cudaMallocAsync(&dev, bytes, ctx->stream));
+        FCP_CUDA(ctx, cudaMemcpyAsync(dev, images, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        int s = enhance_core(ctx, dev, 255.f, n, h, w, gate.data(), nullptr, dev);
+        if (s == FCP_OK && cudaMemcpyAsync(images, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+            s = fail(ctx, FCP_ERR_CUDA, "D2H copy failed");
+        cudaFreeAsync(dev, ctx->stream);
+        FCP_TRY(s);
+    }
+    FCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FCP_OK;
+}
+
+int fcp_enhance_forward(fcp_ctx* ctx, const float* x, int n, int h, int w, float* out) {
+    FCP_TRY(need_model(ctx, FCP_MODEL_RRDBNET));
+    if (!x || !out || n < 1) return fail(ctx, FCP_ERR_INVALID, "fcp_enhance_forward: bad argument");
+    DevIn in;
+    FCP_TRY(in.init(ctx, x, sizeof(float) * 3 * h * w * (size_t)n));
+    DevOut o;
+    FCP_TRY(o.init(ctx, out, sizeof(float) * 3 * 16 * h * w * (size_t)n));
+    FCP_TRY(enhance_core(ctx, in.as<float>(), 1.f, n, h, w, nullptr, o.as<float>(), nullptr));
+    FCP_TRY(o.flush());
+    FCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FCP_OK;
+}
+
+int fcp_pipeline(fcp_ctx* ctx, const uint8_t* images, int n, int h, int w, const int32_t* paddings, float vis_threshold,
+                 float nms_threshold, int strategy, const float* target, int out_w, int out_h, int border_mode,
+                 int allow_skew, int max_faces, float* out_landmarks, int32_t* out_indices, int32_t* out_count,
+                 uint8_t* out_crops, double* out_matrices, uint8_t* out_valid, uint8_t* out_labels, int32_t* out_hist) {
+    FCP_TRY(need_model(ctx, FCP_MODEL_RETINAFACE));
+    const bool do_parse = out_labels || out_hist;
+    if (do_parse) FCP_TRY(need_model(ctx, FCP_MODEL_BISENET));
+    if (!images || n < 1 || max_faces < 1 || !out_count || !target || !out_crops || strategy < 0 || strategy > 2 ||
+        border_mode < 0 || border_mode > 4)
+        return fail(ctx, FCP_ERR_INVALID, "fcp_pipeline: bad argument");
+    DevIn img, pad, tgt;
+    FCP_TRY(img.init(ctx, images, (size_t)n * h * w * 3));
+    FCP_TRY(pad.init(ctx, paddings, sizeof(int32_t) * 4 * n));
+    FCP_TRY(tgt.init(ctx, target, sizeof(float) * 10));
+    float* faces; int32_t* face_img; int32_t* face_count;
+    FCP_CUDA(ctx, cudaMallocAsync(&faces, sizeof(float) * 16 * max_faces, ctx->stream));
+    FCP_CUDA(ctx, cudaMallocAsync(&face_img, sizeof(int32_t) * max_faces, ctx->stream));
+    FCP_CUDA(ctx, cudaMallocAsync(&face_count, sizeof(int32_t), ctx->stream));
+    auto cleanup = [&]() { cudaFreeAsync(faces, ctx->stream); cudaFreeAsync(face_img, ctx->stream); cudaFreeAsync(face_count, ctx->stream); };
+    int s = detect_core(ctx, img.as<uint8_t>(), n, h, w, vis_threshold, nms_threshold, strategy, max_faces, faces, face_img,
+                        face_count, nullptr);
+    if (s != FCP_OK) { cleanup(); return s; }
+    // landmark un-pad (cropper.py:822) happens while unpacking the face records
+    DevOut lms, crops, mats, valid, lab, hist;
+    int32_t count = 0;
+    s = lms.init(ctx, out_landmarks, sizeof(float) * 10 * max_faces, true);
+    if (s == FCP_OK) s = launch_unpack_faces(ctx, faces, face_img, face_count, max_faces, pad.as<int32_t>(), lms.as<float>(), nullptr, nullptr, nullptr);
+    if (s == FCP_OK && cudaMemcpyAsync(&count, face_count, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+        s = fail(ctx, FCP_ERR_CUDA, "count D2H failed");
+    if (s == FCP_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) s = fail(ctx, FCP_ERR_CUDA, "sync failed");
+    if (s != FCP_OK) { cleanup(); return s; }
+    const int f = std::min(count, max_faces);
+    if (f > 0) {
+        s = crops.init(ctx, out_crops, (size_t)f * out_h * out_w * 3);
+        if (s == FCP_OK) s = mats.init(ctx, out_matrices, sizeof(double) * 6 * f, true);
+        if (s == FCP_OK) s = valid.init(ctx, out_valid, f, true);
+        if (s == FCP_OK)
+            s = align_core(ctx, img.as<uint8_t>(), n, h, w, nullptr, nullptr, nullptr, pad.as<int32_t>(), face_img, nullptr,
+                           lms.as<float>(), f, tgt.as<float>(), out_w, out_h, border_mode, allow_skew, crops.as<uint8_t>(),
+                           mats.as<double>(), valid.as<uint8_t>());
+        if (s == FCP_OK && do_parse) {
+            s = lab.init(ctx, out_labels, (size_t)f * out_h * out_w);
+            if (s == FCP_OK) s = hist.init(ctx, out_hist, sizeof(int32_t) * 19 * f);
+            if (s == FCP_OK) s = parse_core(ctx, crops.as<uint8_t>(), f, out_h, out_w, lab.as<uint8_t>(), hist.as<int32_t>(), nullptr);
+        }
+        if (s == FCP_OK) s = lms.flush(sizeof(float) * 10 * f);
+        if (s == FCP_OK) s = crops.flush();
+        if (s == FCP_OK) s = mats.flush();
+        if (s == FCP_OK) s = valid.flush();
+        if (s == FCP_OK) s = lab.flush();
+        if (s == FCP_OK) s = hist.flush();
+        if (s == FCP_OK && out_indices &&
+            cudaMemcpyAsync(out_indices, face_img, sizeof(int32_t) * f,
+                            is_device_ptr(out_indices) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+            s = fail(ctx, FCP_ERR_CUDA, "indices copy failed");
+    }
+    if (s == FCP_OK) {
+        if (is_device_ptr(out_count)) cudaMemcpyAsync(out_count, &count, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
+        else *out_count = count;
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) s = fail(ctx, FCP_ERR_CUDA, "sync failed");
+    }
+    cleanup();
+    if (s == FCP_OK && count > max_faces) return fail(ctx, FCP_ERR_CAPACITY, "max_faces too small: " + std::to_string(count) + " faces found");
+    return s;
+}
+
+int fcp_conv2d(fcp_ctx* ctx, const float* x, int n, int h, int w, int cin, const float* weight, int cout, int k, int stride,
+               int pad, const float* scale, const float* shift, const float* residual, int act, float slope, int impl,
+               float* out) {
+    if (!ctx || !x || !weight || !out || n < 1 || cin < 1 || cout < 1) return fail(ctx, FCP_ERR_INVALID, "fcp_conv2d: bad argument");
+    FCP_CUDA(ctx, cudaSetDevice(ctx->device));
+    Model tmp;
+    HostTensor wt;
+    wt.shape = {cout, cin, k, k};
+    wt.data.assign(weight, weight + (size_t)cout * cin * k * k);
+    tmp.host["c.weight"] = wt;
+    size_t mark = ctx->device_allocs.size();
+    FCP_TRY(pack_conv(ctx, tmp, {"c"}, "", "c"));
+    ConvWeights& cw = tmp.conv["c"];
+    std::vector<float> sc(cw.cout_pad, 1.f), sh(cw.cout_pad, 0.f);
+    if (scale) std::copy(scale, scale + cout, sc.begin());
+    if (shift) std::copy(shift, shift + cout, sh.begin());
+    FCP_CUDA(ctx, cudaMemcpy(cw.scale, sc.data(), sizeof(float) * cw.cout_pad, cudaMemcpyHostToDevice));
+    FCP_CUDA(ctx, cudaMemcpy(cw.shift, sh.data(), sizeof(float) * cw.cout_pad, cudaMemcpyHostToDevice));
+    const int ho = odim(h, k, stride, pad), wo = odim(w, k, stride, pad);
+    const int cs_out = (cout + 3) / 4 * 4;
+    DevIn xin, res;
+    FCP_TRY(xin.init(ctx, x, sizeof(float) * (size_t)n * h * w * cin));
+    FCP_TRY(res.init(ctx, residual, sizeof(float) * (size_t)n * ho * wo * cout));
+    float* dout;
+    FCP_CUDA(ctx, cudaMallocAsync(&dout, sizeof(float) * (size_t)n * ho * wo * cs_out, ctx->stream));
+    ConvOp op;
+    op.in = Tensor{const_cast<float*>(xin.as<float>()), n, h, w, cin, cin, 0};
+    op.out = Tensor{dout, n, ho, wo, cout, cs_out, 0};
+    op.wt = &cw; op.stride = stride; op.pad = pad; op.act = act; op.slope = slope; op.impl = impl;
+    if (residual) { op.res1 = res.as<float>(); op.res1_cs = cout; op.res1_co = 0; }
+    int s = run_conv(ctx, op);
+    if (s == FCP_OK) {
+        cudaError_t e = cudaMemcpy2DAsync(out, sizeof(float) * cout, dout, sizeof(float) * cs_out, sizeof(float) * cout,
+                                          (size_t)n * ho * wo, is_device_ptr(out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                                          ctx->stream);
+        if (e != cudaSuccess) s = fail(ctx, FCP_ERR_CUDA, std::string("conv2d output copy: ") + cudaGetErrorString(e));
+    }
+    cudaFreeAsync(dout, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    for (size_t i = mark; i < ctx->device_allocs.size(); ++i) cudaFree(ctx->device_allocs[i]);
+    ctx->device_allocs.resize(mark);
+    return s;
+}
+
+}  // extern "C"

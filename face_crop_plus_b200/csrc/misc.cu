@@ -1,0 +1,290 @@
+// misc.cu — the non-GEMM layers of the three graphs: stems (Cin=3), pooling, pooled-vector 1x1 convs,
+// channel attention, layout conversion.  All HBM-bound except the stems (fp32 FMA).
+#include "common.h"
+
+namespace fcp {
+
+namespace {
+
+__device__ __forceinline__ float act_fn(float v, int act, float slope) {
+    if (act == FCP_ACT_RELU) return fmaxf(v, 0.f);
+    if (act == FCP_ACT_LRELU) return v > 0.f ? v : v * slope;
+    if (act == FCP_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------ stem 7x7/s2
+// body.conv1+bn1+relu (torchvision resnet.py:268-270) and cp.resnet.conv1+bn1+relu (_layers.py:262-263).
+// CTA = 8x32 output pixels x 64 channels; input patch 21x69x3 and the 147x64 filter bank live in shared memory.
+constexpr int ST_TH = 8, ST_TW = 32, ST_PH = (ST_TH - 1) * 2 + 7, ST_PW = (ST_TW - 1) * 2 + 7;
+
+template <int MODE>
+__global__ void __launch_bounds__(256) stem7_kernel(const void* __restrict__ src, int N, int H, int W,
+                                                    const float* __restrict__ wkn, const float* __restrict__ scale,
+                                                    const float* __restrict__ shift, float* __restrict__ out, int Ho,
+                                                    int Wo, int out_cs, int out_co) {
+    extern __shared__ __align__(16) float sm[];
+    float* sw = sm;                       // [147][64]
+    float* sp = sm + 147 * 64;            // [ST_PH][ST_PW][3]
+    const int tid = threadIdx.x;
+    const int n = blockIdx.z;
+    const int ho0 = blockIdx.y * ST_TH, wo0 = blockIdx.x * ST_TW;
+    for (int i = tid; i < 147 * 64 / 4; i += 256)
+        reinterpret_cast<float4*>(sw)[i] = reinterpret_cast<const float4*>(wkn)[i];
+    const int hi0 = ho0 * 2 - 3, wi0 = wo0 * 2 - 3;
+    for (int i = tid; i < ST_PH * ST_PW * 3; i += 256) {
+        int c = i % 3;
+        int t = i / 3;
+        int px = t % ST_PW, py = t / ST_PW;
+        int hi = hi0 + py, wi = wi0 + px;
+        float v = 0.f;
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W) {
+            size_t pix = ((size_t)n * H + hi) * W + wi;
+            if (MODE == 0) {
+                // RGB uint8 -> BGR, minus (104,117,123): retinaface.py:450-451
+                const uint8_t* s8 = static_cast<const uint8_t*>(src);
+                const float mean = c == 0 ? 104.f : (c == 1 ? 117.f : 123.f);
+                v = (float)s8[pix * 3 + (2 - c)] - mean;
+            } else {
+                v = static_cast<const float*>(src)[pix * 3 + c];
+            }
+        }
+        sp[i] = v;
+    }
+    __syncthreads();
+    const int tx = tid % ST_TW, ty = tid / ST_TW;
+    float acc[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+    for (int r = 0; r < 7; ++r) {
+        for (int s = 0; s < 7; ++s) {
+            const float* pin = sp + ((ty * 2 + r) * ST_PW + tx * 2 + s) * 3;
+            const float* pw = sw + (r * 7 + s) * 3 * 64;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float x = pin[c];
+#pragma unroll
+                for (int j = 0; j < 64; j += 4) {
+                    float4 w4 = *reinterpret_cast<const float4*>(pw + c * 64 + j);
+                    acc[j] = fmaf(x, w4.x, acc[j]);
+                    acc[j + 1] = fmaf(x, w4.y, acc[j + 1]);
+                    acc[j + 2] = fmaf(x, w4.z, acc[j + 2]);
+                    acc[j + 3] = fmaf(x, w4.w, acc[j + 3]);
+                }
+            }
+        }
+    }
+    int ho = ho0 + ty, wo = wo0 + tx;
+    if (ho < Ho && wo < Wo) {
+        float* dst = out + (((size_t)n * Ho + ho) * Wo + wo) * out_cs + out_co;
+#pragma unroll
+        for (int j = 0; j < 64; j += 4) {
+            float4 o;
+            o.x = fmaxf(acc[j] * scale[j] + shift[j], 0.f);
+            o.y = fmaxf(acc[j + 1] * scale[j + 1] + shift[j + 1], 0.f);
+            o.z = fmaxf(acc[j + 2] * scale[j + 2] + shift[j + 2], 0.f);
+            o.w = fmaxf(acc[j + 3] * scale[j + 3] + shift[j + 3], 0.f);
+            *reinterpret_cast<float4*>(dst + j) = o;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------- RRDB conv_first (3x3, Cin=3)
+// rrdb.py:77 conv_first on images/255 (rrdb.py:142); input f32 NCHW, output NHWC 64 channels, bias only.
+__global__ void __launch_bounds__(256) conv3_first_kernel(const float* __restrict__ src, float in_div, int N, int H,
+                                                          int W, const float* __restrict__ wkn,
+                                                          const float* __restrict__ shift, float* __restrict__ out,
+                                                          int out_cs, int out_co) {
+    __shared__ __align__(16) float sw[27 * 64];
+    for (int i = threadIdx.x; i < 27 * 64; i += 256) sw[i] = wkn[i];
+    __syncthreads();
+    size_t pix = (size_t)blockIdx.x * 256 + threadIdx.x;
+    size_t total = (size_t)N * H * W;
+    if (pix >= total) return;
+    int wq = pix % W;
+    size_t t = pix / W;
+    int hq = t % H;
+    int n = t / H;
+    float acc[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) acc[j] = shift[j];
+    for (int r = 0; r < 3; ++r)
+        for (int s = 0; s < 3; ++s) {
+            int hi = hq + r - 1, wi = wq + s - 1;
+            if (hi < 0 || hi >= H || wi < 0 || wi >= W) continue;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float x = __fdiv_rn(src[(((size_t)n * 3 + c) * H + hi) * W + wi], in_div);
+                const float* pw = sw + ((r * 3 + s) * 3 + c) * 64;
+#pragma unroll
+                for (int j = 0; j < 64; ++j) acc[j] = fmaf(x, pw[j], acc[j]);
+            }
+        }
+    float* dst = out + pix * out_cs + out_co;
+#pragma unroll
+    for (int j = 0; j < 64; j += 4)
+        *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+}
+
+// ------------------------------------------------------------------------------------------- maxpool 3x3/s2/p1
+__global__ void maxpool3s2_kernel(const float* __restrict__ in, int N, int H, int W, int C, int in_cs, int in_co,
+                                  float* __restrict__ out, int Ho, int Wo, int out_cs, int out_co) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int c4n = C / 4;
+    size_t total = (size_t)N * Ho * Wo * c4n;
+    if (idx >= total) return;
+    int c4 = idx % c4n;
+    size_t p = idx / c4n;
+    int wo = p % Wo;
+    size_t t = p / Wo;
+    int ho = t % Ho;
+    int n = t / Ho;
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int r = 0; r < 3; ++r) {
+        int hi = ho * 2 - 1 + r;
+        if (hi < 0 || hi >= H) continue;
+        for (int s = 0; s < 3; ++s) {
+            int wi = wo * 2 - 1 + s;
+            if (wi < 0 || wi >= W) continue;
+            float4 v = *reinterpret_cast<const float4*>(in + (((size_t)n * H + hi) * W + wi) * in_cs + in_co + c4 * 4);
+            m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+        }
+    }
+    *reinterpret_cast<float4*>(out + p * out_cs + out_co + c4 * 4) = m;
+}
+
+// ------------------------------------------------------------------------------------- global average pooling
+// F.avg_pool2d(x, x.size()[2:]) (_layers.py:307,332,360).  grid (C/32, N), block 32x8.
+__global__ void global_avgpool_kernel(const float* __restrict__ in, int HW, int cs, int co, int C,
+                                      float* __restrict__ out) {
+    __shared__ float red[8][33];
+    int c = blockIdx.x * 32 + threadIdx.x;
+    int n = blockIdx.y;
+    float s = 0.f;
+    const float* base = in + (size_t)n * HW * cs + co + c;
+    for (int p = threadIdx.y; p < HW; p += 8) s += base[(size_t)p * cs];
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0) {
+        float tot = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tot += red[i][threadIdx.x];
+        out[(size_t)n * C + c] = tot / (float)HW;
+    }
+}
+
+// ------------------------------------------------------------- 1x1 conv on pooled vectors (+BN fold, activation)
+__global__ void fc_kernel(const float* __restrict__ in, int cin, const float* __restrict__ wkn, int cout_pad,
+                          int cout, const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                          float* __restrict__ out) {
+    int co = blockIdx.x * blockDim.x + threadIdx.x;
+    int n = blockIdx.y;
+    if (co >= cout) return;
+    float s = 0.f;
+    const float* x = in + (size_t)n * cin;
+    for (int ci = 0; ci < cin; ++ci) s = fmaf(x[ci], wkn[(size_t)ci * cout_pad + co], s);
+    out[(size_t)n * cout + co] = act_fn(s * scale[co] + shift[co], act, 0.f);
+}
+
+// --------------------------------------------------- out = in * mul[n][c] (+ addvec[n][c]) (+ in), NHWC float4
+__global__ void channel_affine_kernel(const float* __restrict__ in, int in_cs, int in_co, size_t HW, int C,
+                                      const float* __restrict__ mul, const float* __restrict__ addv, int add_self,
+                                      float* __restrict__ out, int out_cs, int out_co, size_t total) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int c4n = C / 4;
+    int c = (idx % c4n) * 4;
+    size_t p = idx / c4n;
+    int n = p / HW;
+    float4 v = *reinterpret_cast<const float4*>(in + p * in_cs + in_co + c);
+    float4 m = *reinterpret_cast<const float4*>(mul + (size_t)n * C + c);
+    float4 o = make_float4(v.x * m.x, v.y * m.y, v.z * m.z, v.w * m.w);
+    if (addv) {
+        float4 a = *reinterpret_cast<const float4*>(addv + (size_t)n * C + c);
+        o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+    }
+    if (add_self) { o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w; }
+    *reinterpret_cast<float4*>(out + p * out_cs + out_co + c) = o;
+}
+
+// ----------------------------------------------------------------------------------------- layout conversions
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, int HW, int C, int cs, int co,
+                                    float* __restrict__ out, size_t total) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // over n*c*hw, hw fastest (coalesced writes)
+    if (idx >= total) return;
+    int p = idx % HW;
+    size_t t = idx / HW;
+    int c = t % C;
+    size_t n = t / C;
+    out[idx] = in[(n * HW + p) * cs + co + c];
+}
+
+}  // namespace
+
+int launch_stem7(fcp_ctx* ctx, const void* src, int mode, int n, int h, int w, const float* w_kn, const float* scale,
+                 const float* shift, Tensor out) {
+    size_t smem = (147 * 64 + ST_PH * ST_PW * 3) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        FCP_CUDA(ctx, cudaFuncSetAttribute(stem7_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FCP_CUDA(ctx, cudaFuncSetAttribute(stem7_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid((out.w + ST_TW - 1) / ST_TW, (out.h + ST_TH - 1) / ST_TH, n);
+    if (mode == 0)
+        stem7_kernel<0><<<grid, 256, smem, ctx->stream>>>(src, n, h, w, w_kn, scale, shift, out.p, out.h, out.w, out.cs, out.co);
+    else
+        stem7_kernel<1><<<grid, 256, smem, ctx->stream>>>(src, n, h, w, w_kn, scale, shift, out.p, out.h, out.w, out.cs, out.co);
+    FCP_KERNEL_CHECK(ctx);
+    return FCP_OK;
+}
+
+int launch_conv3_first(fcp_ctx* ctx, const float* src_nchw, float in_div, int n, int h, int w, const float* w_kn,
+                       const float* shift, Tensor out) {
+    size_t total = (size_t)n * h * w;
+    conv3_first_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(src_nchw, in_div, n, h, w, w_kn, shift,
+                                                                                 out.p, out.cs, out.co);
+    FCP_KERNEL_CHECK(ctx);
+    return FCP_OK;
+}
+
+int launch_maxpool3s2(fcp_ctx* ctx, Tensor in, Tensor out) {
+    size_t total = out.pixels() * (in.c / 4);
+    maxpool3s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(in.p, in.n, in.h, in.w, in.c, in.cs, in.co,
+                                                                               out.p, out.h, out.w, out.cs, out.co);
+    FCP_KERNEL_CHECK(ctx);
+    return FCP_OK;
+}
+
+int launch_global_avgpool(fcp_ctx* ctx, Tensor in, float* out_nc) {
+    if (in.c % 32) return fail(ctx, FCP_ERR_INVALID, "avgpool: C must be a multiple of 32");
+    dim3 grid(in.c / 32, in.n), block(32, 8);
+    global_avgpool_kernel<<<grid, block, 0, ctx->stream>>>(in.p, in.h * in.w, in.cs, in.co, in.c, out_nc);
+    FCP_KERNEL_CHECK(ctx);
+    return FCP_OK;
+}
+
+int launch_fc(fcp_ctx* ctx, const float* in_nc, int n, int cin, const ConvWeights* wt, int act, float* out_nc) {
+    dim3 grid((wt->cout + 127) / 128, n);
+    fc_kernel<<<grid, 128, 0, ctx->stream>>>(in_nc, cin, wt->w_kn, wt->cout_pad, wt->cout, wt->scale, wt->shift, act, out_nc);
+    FCP_KERNEL_CHECK(ctx);
+    return FCP_OK;
+}
+
+int launch_channel_affine(fcp_ctx* ctx, Tensor in, const float* mul_nc, const float* addvec_nc, int add_self,
+                          Tensor out) {
+    size_t total = in.pixels() * (in.c / 4);
+    channel_affine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(
+        in.p, in.cs, in.co, (size_t)in.h * in.w, in.c, mul_nc, addvec_nc, add_self, out.p, out.cs, out.co, total);
+    FCP_KERNEL_CHECK(ctx);
+    return FCP_OK;
+}
+
+int launch_nhwc_to_nchw(fcp_ctx* ctx, const float* in, int n, int h, int w, int c, int cs, float* out) {
+    size_t total = (size_t)n * c * h * w;
+    nhwc_to_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(in, h * w, c, cs, 0, out, total);
+    FCP_KERNEL_CHECK(ctx);
+    return FCP_OK;
+}
+
+}  // namespace fcp

@@ -1,0 +1,325 @@
+// runtime.cu — context, stream-ordered arena, weight ingestion (BN folding + packing) and small host helpers.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "common.h"
+#include "graphs.h"
+
+namespace fcp {
+
+int fail(fcp_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->error = msg;
+    return code;
+}
+
+// ------------------------------------------------------------------------------------------------------ Arena
+Arena::~Arena() {
+    if (base_) cudaFree(base_);
+}
+
+bool Arena::reserve(size_t bytes) {
+    if (bytes <= cap_ && base_) return true;
+    if (base_) {
+        cudaDeviceSynchronize();
+        cudaFree(base_);
+        base_ = nullptr;
+    }
+    if (cudaMalloc(&base_, bytes) != cudaSuccess) {
+        cap_ = 0;
+        base_ = nullptr;
+        return false;
+    }
+    cap_ = bytes;
+    reset();
+    return true;
+}
+
+void Arena::reset() {
+    blocks_.clear();
+    blocks_.push_back({0, plan_ ? (size_t)1 << 60 : cap_, false});
+}
+
+void Arena::set_plan_mode(bool on) {
+    plan_ = on;
+    high_ = 0;
+    reset();
+}
+
+void* Arena::alloc(size_t bytes) {
+    bytes = (bytes + 1023) & ~(size_t)1023;
+    for (size_t i = 0; i < blocks_.size(); ++i) {
+        Block& b = blocks_[i];
+        if (b.used || b.size < bytes) continue;
+        size_t off = b.off;
+        if (b.size > bytes) {
+            Block rest{b.off + bytes, b.size - bytes, false};
+            b.size = bytes;
+            b.used = true;
+            blocks_.insert(blocks_.begin() + i + 1, rest);
+        } else {
+            b.used = true;
+        }
+        high_ = std::max(high_, off + bytes);
+        // plan mode hands out fake (never dereferenced) addresses above a non-null base
+        return (plan_ ? reinterpret_cast<char*>((uintptr_t)1 << 40) : base_) + off;
+    }
+    return nullptr;
+}
+
+void Arena::free(void* p) {
+    if (!p) return;
+    size_t off = static_cast<char*>(p) - (plan_ ? reinterpret_cast<char*>((uintptr_t)1 << 40) : base_);
+    for (size_t i = 0; i < blocks_.size(); ++i) {
+        if (blocks_[i].off != off) continue;
+        blocks_[i].used = false;
+        if (i + 1 < blocks_.size() && !blocks_[i + 1].used) {
+            blocks_[i].size += blocks_[i + 1].size;
+            blocks_.erase(blocks_.begin() + i + 1);
+        }
+        if (i > 0 && !blocks_[i - 1].used) {
+            blocks_[i - 1].size += blocks_[i].size;
+            blocks_.erase(blocks_.begin() + i);
+        }
+        return;
+    }
+}
+
+// --------------------------------------------------------------------------------------------- weight helpers
+static const HostTensor* find(const Model& m, const std::string& key) {
+    auto it = m.host.find(key);
+    return it == m.host.end() ? nullptr : &it->second;
+}
+
+static int upload(fcp_ctx* ctx, const std::vector<float>& v, float** out) {
+    FCP_CUDA(ctx, cudaMalloc(out, v.size() * sizeof(float)));
+    ctx->device_allocs.push_back(*out);
+    FCP_CUDA(ctx, cudaMemcpy(*out, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return FCP_OK;
+}
+
+static inline float tf32_trunc(float x) {
+    uint32_t u;
+    std::memcpy(&u, &x, 4);
+    u &= 0xFFFFE000u;
+    float r;
+    std::memcpy(&r, &u, 4);
+    return r;
+}
+
+// Packs conv `convs[i].weight` (OIHW, concatenated along Cout) with optional bias and optional BatchNorm `bn`
+// (running stats folded like ATen's eval batch_norm: alpha = gamma/sqrt(var+eps), beta = bias - mean*alpha).
+int pack_conv(fcp_ctx* ctx, Model& m, const std::vector<std::string>& convs, const std::string& bn,
+              const std::string& name) {
+    ConvWeights cw;
+    std::vector<const HostTensor*> ws, bs;
+    for (auto& c : convs) {
+        const HostTensor* w = find(m, c + ".weight");
+        if (!w || w->shape.size() != 4) return fail(ctx, FCP_ERR_STATE, "missing conv weight: " + c + ".weight");
+        ws.push_back(w);
+        bs.push_back(find(m, c + ".bias"));
+        if (cw.cin == 0) { cw.cin = (int)w->shape[1]; cw.k = (int)w->shape[2]; }
+        if (w->shape[1] != cw.cin || w->shape[2] != cw.k || w->shape[3] != cw.k)
+            return fail(ctx, FCP_ERR_INVALID, "conv shapes of a fused group differ: " + c);
+        cw.cout += (int)w->shape[0];
+    }
+    cw.cout_pad = (cw.cout + 31) / 32 * 32;
+    const int K = cw.k * cw.k * cw.cin;
+    std::vector<float> wkn((size_t)K * cw.cout_pad, 0.f), scale(cw.cout_pad, 1.f), shift(cw.cout_pad, 0.f);
+    std::vector<float> whi((size_t)cw.cout_pad * K, 0.f), wlo((size_t)cw.cout_pad * K, 0.f);
+    int o0 = 0;
+    for (size_t g = 0; g < ws.size(); ++g) {
+        const HostTensor& w = *ws[g];
+        int co_n = (int)w.shape[0];
+        for (int o = 0; o < co_n; ++o)
+            for (int c = 0; c < cw.cin; ++c)
+                for (int r = 0; r < cw.k; ++r)
+                    for (int s = 0; s < cw.k; ++s) {
+                        float v = w.data[(((size_t)o * cw.cin + c) * cw.k + r) * cw.k + s];
+                        size_t kk = (size_t)(r * cw.k + s) * cw.cin + c;
+                        wkn[kk * cw.cout_pad + o0 + o] = v;
+                        float hi = tf32_trunc(v);
+                        whi[(size_t)(o0 + o) * K + kk] = hi;
+                        wlo[(size_t)(o0 + o) * K + kk] = v - hi;
+                    }
+        if (bs[g])
+            for (int o = 0; o < co_n; ++o) shift[o0 + o] = bs[g]->data[o];
+        o0 += co_n;
+    }
+    if (!bn.empty()) {
+        const HostTensor *g = find(m, bn + ".weight"), *b = find(m, bn + ".bias"), *mu = find(m, bn + ".running_mean"),
+                         *var = find(m, bn + ".running_var");
+        if (!g || !b || !mu || !var || (int)g->data.size() != cw.cout)
+            return fail(ctx, FCP_ERR_STATE, "missing/mismatched BatchNorm tensors: " + bn);
+        for (int o = 0; o < cw.cout; ++o) {
+            float invstd = 1.0f / std::sqrt(var->data[o] + 1e-5f);
+            float alpha = g->data[o] * invstd;
+            float beta = b->data[o] - mu->data[o] * alpha;
+            shift[o] = shift[o] * alpha + beta;   // conv bias (0 here) goes through the BN as well
+            scale[o] = alpha;
+        }
+    }
+    FCP_TRY(upload(ctx, wkn, &cw.w_kn));
+    FCP_TRY(upload(ctx, whi, &cw.w_hi));
+    FCP_TRY(upload(ctx, wlo, &cw.w_lo));
+    FCP_TRY(upload(ctx, scale, &cw.scale));
+    FCP_TRY(upload(ctx, shift, &cw.shift));
+    m.conv[name] = cw;
+    return FCP_OK;
+}
+
+// ------------------------------------------------------------------------------------- host/device staging
+bool is_device_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int DevIn::init(fcp_ctx* ctx, const void* src, size_t bytes) {
+    ctx_ = ctx;
+    if (!src || bytes == 0) { p_ = nullptr; return FCP_OK; }
+    if (is_device_ptr(src)) { p_ = const_cast<void*>(src); return FCP_OK; }
+    FCP_CUDA(ctx, cudaMallocAsync(&p_, bytes, ctx->stream));
+    owned_ = true;
+    FCP_CUDA(ctx, cudaMemcpyAsync(p_, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return FCP_OK;
+}
+DevIn::~DevIn() {
+    if (owned_ && p_) cudaFreeAsync(p_, ctx_->stream);
+}
+
+int DevOut::init(fcp_ctx* ctx, void* dst, size_t bytes, bool need_scratch) {
+    ctx_ = ctx; dst_ = dst; bytes_ = bytes;
+    if (bytes == 0) return FCP_OK;
+    if (dst && is_device_ptr(dst)) { p_ = dst; return FCP_OK; }
+    if (!dst && !need_scratch) return FCP_OK;
+    FCP_CUDA(ctx, cudaMallocAsync(&p_, bytes, ctx->stream));
+    owned_ = true;
+    return FCP_OK;
+}
+int DevOut::flush(size_t bytes) {
+    if (owned_ && dst_ && p_) {
+        size_t nbytes = bytes == (size_t)-1 ? bytes_ : std::min(bytes, bytes_);
+        if (nbytes) FCP_CUDA(ctx_, cudaMemcpyAsync(dst_, p_, nbytes, cudaMemcpyDeviceToHost, ctx_->stream));
+    }
+    return FCP_OK;
+}
+DevOut::~DevOut() {
+    if (owned_ && p_) cudaFreeAsync(p_, ctx_->stream);
+}
+
+int run_conv(fcp_ctx* ctx, const ConvOp& op) {
+    return op.impl == 1 ? launch_conv_tc(ctx, op) : launch_conv_ffma(ctx, op);
+}
+
+}  // namespace fcp
+
+// ================================================================================================ C ABI: core
+using namespace fcp;
+
+extern "C" {
+
+const char* fcp_version(void) { return "fcp_b200 0.1.0 sm_100a"; }
+
+int fcp_create(int device, fcp_ctx** out) {
+    if (!out) return FCP_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return FCP_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return FCP_ERR_CUDA;
+    fcp_ctx* ctx = new fcp_ctx();
+    ctx->device = device;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return FCP_ERR_CUDA;
+    }
+    ctx->own_stream = true;
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    const char* tc = getenv("FCP_CONV_IMPL");
+    if (tc) ctx->use_tc = atoi(tc);
+    *out = ctx;
+    return FCP_OK;
+}
+
+void fcp_destroy(fcp_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (void* p : ctx->device_allocs) cudaFree(p);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* fcp_last_error(const fcp_ctx* ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+
+int fcp_set_stream(fcp_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return FCP_ERR_INVALID;
+    if (ctx->own_stream && ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+    }
+    ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    ctx->own_stream = false;
+    return FCP_OK;
+}
+
+int fcp_sync(fcp_ctx* ctx) {
+    if (!ctx) return FCP_ERR_INVALID;
+    FCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FCP_OK;
+}
+
+int64_t fcp_launch_count(const fcp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int fcp_set_micro_batch(fcp_ctx* ctx, int detect_images, int parse_faces) {
+    if (!ctx || detect_images < 1 || parse_faces < 1) return fail(ctx, FCP_ERR_INVALID, "micro batch sizes must be >= 1");
+    ctx->det_mb = detect_images;
+    ctx->par_mb = parse_faces;
+    return FCP_OK;
+}
+
+int fcp_set_conv_impl(fcp_ctx* ctx, int impl) {
+    if (!ctx || impl < 0 || impl > 1) return fail(ctx, FCP_ERR_INVALID, "conv impl must be 0 or 1");
+    ctx->use_tc = impl;
+    return FCP_OK;
+}
+
+int fcp_load_tensor(fcp_ctx* ctx, int model, const char* key, const float* host_data, const int64_t* shape, int ndim) {
+    if (!ctx || model < 0 || model > 2 || !key || !host_data || ndim < 0 || ndim > 8)
+        return fail(ctx, FCP_ERR_INVALID, "fcp_load_tensor: bad argument");
+    HostTensor t;
+    size_t count = 1;
+    for (int i = 0; i < ndim; ++i) {
+        t.shape.push_back(shape[i]);
+        count *= (size_t)shape[i];
+    }
+    t.data.assign(host_data, host_data + count);
+    ctx->models[model].host[key] = std::move(t);
+    ctx->models[model].finalized = false;
+    return FCP_OK;
+}
+
+int fcp_finalize(fcp_ctx* ctx, int model, int rrdb_blocks) {
+    if (!ctx || model < 0 || model > 2) return fail(ctx, FCP_ERR_INVALID, "fcp_finalize: bad model id");
+    FCP_CUDA(ctx, cudaSetDevice(ctx->device));
+    Model& m = ctx->models[model];
+    m.conv.clear();
+    m.rrdb_blocks = rrdb_blocks > 0 ? rrdb_blocks : 23;
+    int s = model == FCP_MODEL_RETINAFACE ? finalize_retinaface(ctx)
+          : model == FCP_MODEL_BISENET  ? finalize_bisenet(ctx) : finalize_rrdbnet(ctx);
+    if (s != FCP_OK) return s;
+    m.finalized = true;
+    m.host.clear();   // host copies are no longer needed
+    return FCP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,139 @@
+/*
+ * fcp_b200.h — C ABI of libfcpb200.so, the B200 (sm_100a) implementation of the face-crop-plus hot path
+ * (detect -> align -> [enhance] -> parse).
+ *
+ * The reference (mantasu/face-crop-plus, pure Python) has no FFI of its own: the path sits behind Python
+ * objects.  Each entry point below replaces one of those Python call sites; the host mirror in
+ * face_crop_plus_b200/ binds them with ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *  - every function returns an int status (FCP_OK == 0); fcp_last_error(ctx) gives the message;
+ *  - no exceptions, no ownership transfer: inputs are borrowed, outputs are caller-allocated with explicit capacities;
+ *  - every data pointer may be HOST or DEVICE memory (queried with cudaPointerGetAttributes); host buffers are
+ *    staged through pinned memory inside the call, so host<->device copies are part of the call;
+ *  - images / crops are uint8 NHWC RGB; landmarks are float32 (x, y) pairs; matrices are float64 2x3 row-major;
+ *  - a context is bound to one CUDA device and one stream and is thread-compatible (one context per worker thread).
+ */
+#ifndef FCP_B200_H
+#define FCP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FCP_OK 0
+#define FCP_ERR_INVALID 1   /* bad argument / unknown key / unsupported shape                           */
+#define FCP_ERR_CUDA 2      /* a CUDA runtime call or kernel failed                                      */
+#define FCP_ERR_STATE 3     /* model not finalized, weights missing                                      */
+#define FCP_ERR_CAPACITY 4  /* an output capacity was too small (counts are still written; call again)   */
+
+typedef struct fcp_ctx fcp_ctx;
+
+/* model ids: models/retinaface.py:10, models/bise.py:8, models/rrdb.py:8 */
+enum { FCP_MODEL_RETINAFACE = 0, FCP_MODEL_BISENET = 1, FCP_MODEL_RRDBNET = 2 };
+/* RetinaFace.take_by_strategy, models/retinaface.py:306-408 */
+enum { FCP_STRATEGY_ALL = 0, FCP_STRATEGY_BEST = 1, FCP_STRATEGY_LARGEST = 2 };
+/* cv2.BORDER_* values reachable through Cropper(padding=...), cropper.py:512 */
+enum { FCP_BORDER_CONSTANT = 0, FCP_BORDER_REPLICATE = 1, FCP_BORDER_REFLECT = 2, FCP_BORDER_WRAP = 3,
+       FCP_BORDER_REFLECT_101 = 4 };
+/* activation codes of fcp_conv2d */
+enum { FCP_ACT_NONE = 0, FCP_ACT_RELU = 1, FCP_ACT_LRELU = 2, FCP_ACT_SIGMOID = 3 };
+
+/* ---- lifetime --------------------------------------------------------------------------------------- */
+int fcp_create(int device, fcp_ctx** out);
+void fcp_destroy(fcp_ctx* ctx);
+const char* fcp_last_error(const fcp_ctx* ctx);
+/* ABI/version string of the library ("fcp_b200 <semver> sm_100a") */
+const char* fcp_version(void);
+/* use an existing cudaStream_t (e.g. torch's current stream) instead of the context's own stream */
+int fcp_set_stream(fcp_ctx* ctx, void* cuda_stream);
+/* block until all work queued by this context has finished */
+int fcp_sync(fcp_ctx* ctx);
+/* number of kernels this context has launched since creation (bench.py reports it as gpu_launches) */
+int64_t fcp_launch_count(const fcp_ctx* ctx);
+/* images per detector micro-batch / faces per parser micro-batch (bounds the activation arena; default 8 / 32) */
+int fcp_set_micro_batch(fcp_ctx* ctx, int detect_images, int parse_faces);
+/* convolution kernel used by the model graphs: 0 = CUDA-core fp32, 1 = tcgen05 3xTF32 (same results to fp32 rounding) */
+int fcp_set_conv_impl(fcp_ctx* ctx, int impl);
+
+/* ---- weights: replaces LoadMixin.load / get_weights (models/_layers.py:16-35) ---------------------------
+ * Feed every entry of the reference state_dict (same keys, float32, host memory, OIHW conv weights), then
+ * finalize: BN running stats are folded into per-channel scale/shift, conv weights are re-packed for the
+ * kernels and uploaded.  num_batches_tracked entries may be skipped.  rrdb_blocks: RRDB_trunk length (23). */
+int fcp_load_tensor(fcp_ctx* ctx, int model, const char* key, const float* host_data, const int64_t* shape, int ndim);
+int fcp_finalize(fcp_ctx* ctx, int model, int rrdb_blocks);
+
+/* ---- detect: replaces RetinaFace.predict (models/retinaface.py:410-470) ---------------------------------
+ * images  u8 [n,h,w,3] RGB (what utils.as_batch produces, before as_tensor's float conversion; h,w % 32 == 0 not
+ *         required).  Outputs, ordered by image then by the strategy's order, capacity max_faces:
+ * out_landmarks f32 [max_faces,5,2] (batch pixel coords), out_indices i32 [max_faces] image index per face,
+ * out_boxes f32 [max_faces,4] x1y1x2y2, out_scores f32 [max_faces], out_anchors i32 [max_faces] prior index,
+ * out_count i32 [1] number of faces (written even on FCP_ERR_CAPACITY).  Any output pointer except out_count
+ * and out_landmarks/out_indices may be NULL. */
+int fcp_detect(fcp_ctx* ctx, const uint8_t* images, int n, int h, int w, float vis_threshold, float nms_threshold,
+               int strategy, int max_faces, float* out_landmarks, int32_t* out_indices, float* out_boxes,
+               float* out_scores, int32_t* out_anchors, int32_t* out_count);
+/* raw head outputs of RetinaFace.forward before softmax (models/retinaface.py:137-142):
+ * out_heads f32 [n, A, 16] = (cls[2], box[4], ldm[10]) per prior, priors in the reference order (level,row,col,anchor) */
+int fcp_detect_heads(fcp_ctx* ctx, const uint8_t* images, int n, int h, int w, float* out_heads);
+/* decode + threshold + NMS + strategy on given head outputs (models/retinaface.py:146-408, _layers.py:41-62) */
+int fcp_detect_post(fcp_ctx* ctx, const float* heads, int n, int h, int w, float vis_threshold, float nms_threshold,
+                    int strategy, int max_faces, float* out_landmarks, int32_t* out_indices, float* out_boxes,
+                    float* out_scores, int32_t* out_anchors, int32_t* out_count);
+
+/* ---- align: replaces Cropper.crop_align (cropper.py:441-552) --------------------------------------------
+ * images u8 [n,h,w,3]; paddings i32 [n,4] = (top,bottom,left,right) or NULL; indices i32 [f]; landmarks f32 [f,5,2]
+ * (already un-padded, cropper.py:822); target f32 [5,2] (cropper.py:392-439).  out_crops u8 [f,out_h,out_w,3]
+ * is written for EVERY face slot (invalid faces are zero-filled; the host drops them like cropper.py:529-531),
+ * out_matrices f64 [f,2,3] (may be NULL), out_valid u8 [f] (may be NULL). */
+int fcp_align(fcp_ctx* ctx, const uint8_t* images, int n, int h, int w, const int32_t* paddings,
+              const int32_t* indices, const float* landmarks, int f, const float* target, int out_w, int out_h,
+              int border_mode, int allow_skew, uint8_t* out_crops, double* out_matrices, uint8_t* out_valid);
+/* same, for a ragged list of images (landmarks-only path, cropper.py:796-813): image_ptrs[i] is u8 [hs[i],ws[i],3] */
+int fcp_align_list(fcp_ctx* ctx, const uint8_t* const* image_ptrs, const int32_t* hs, const int32_t* ws, int n,
+                   const int32_t* paddings, const int32_t* indices, const float* landmarks, int f,
+                   const float* target, int out_w, int out_h, int border_mode, int allow_skew, uint8_t* out_crops,
+                   double* out_matrices, uint8_t* out_valid);
+
+/* ---- parse: replaces BiSeNet.predict (models/bise.py:327-418) -------------------------------------------
+ * crops u8 [f,h,w,3]; out_labels u8 [f,h,w] (argmax class 0..18), out_hist i32 [f,19] pixel count per class
+ * (either may be NULL).  Grouping by thresholds (bise.py:214-325) is integer work on out_hist done by the host;
+ * fcp_masks writes the 0/255 masks of one mask group: out_masks u8 [f,h,w] = 255 where class_lut[label] != 0. */
+int fcp_parse(fcp_ctx* ctx, const uint8_t* crops, int f, int h, int w, uint8_t* out_labels, int32_t* out_hist);
+/* BiSeNet logits at 1/8 resolution before the final upsample: out_logits f32 [f,19,64,64] NCHW (bise.py:211) */
+int fcp_parse_logits(fcp_ctx* ctx, const uint8_t* crops, int f, int h, int w, float* out_logits);
+/* the tail only: bilinear(align_corners) to 512x512 -> nearest to (h,w) -> argmax, on given logits (bise.py:212,394) */
+int fcp_parse_tail(fcp_ctx* ctx, const float* logits, int f, int h, int w, uint8_t* out_labels, int32_t* out_hist);
+int fcp_masks(fcp_ctx* ctx, const uint8_t* labels, int f, int h, int w, const uint8_t* class_lut19, uint8_t* out_masks);
+
+/* ---- enhance: replaces RRDBNet.predict / forward (models/rrdb.py:64-146) --------------------------------
+ * images f32 [n,3,h,w] NCHW, 0..255 (the tensor Cropper hands over, cropper.py:835); enhanced IN PLACE where
+ * do_enhance[i] != 0 (gate computed by the host from landmarks, rrdb.py:125-140; NULL = all). */
+int fcp_enhance(fcp_ctx* ctx, float* images, int n, int h, int w, const uint8_t* do_enhance);
+/* RRDBNet.forward: x f32 [n,3,h,w] in [0,1] -> out f32 [n,3,4h,4w] */
+int fcp_enhance_forward(fcp_ctx* ctx, const float* x, int n, int h, int w, float* out);
+
+/* ---- whole path: the detect branch of Cropper.process_batch (cropper.py:815-847) in one call ------------
+ * detect -> un-pad -> align -> parse with no host round trip between the stages.  Capacities as in fcp_detect;
+ * out_crops u8 [max_faces,out_h,out_w,3], out_labels u8 [max_faces,out_h,out_w] (NULL = skip parsing),
+ * out_hist i32 [max_faces,19], out_matrices f64 [max_faces,2,3], out_valid u8 [max_faces]. */
+int fcp_pipeline(fcp_ctx* ctx, const uint8_t* images, int n, int h, int w, const int32_t* paddings,
+                 float vis_threshold, float nms_threshold, int strategy, const float* target, int out_w, int out_h,
+                 int border_mode, int allow_skew, int max_faces, float* out_landmarks, int32_t* out_indices,
+                 int32_t* out_count, uint8_t* out_crops, double* out_matrices, uint8_t* out_valid,
+                 uint8_t* out_labels, int32_t* out_hist);
+
+/* ---- kernel-level test hook: one fused convolution (what nn.Conv2d + BatchNorm2d + activation do in the
+ * reference graphs).  x f32 NHWC [n,h,w,cin]; weight f32 OIHW host [cout,cin,k,k]; scale/shift f32 [cout] host
+ * (NULL = 1/0); residual f32 NHWC [n,ho,wo,cout] added before the activation (NULL = none);
+ * out f32 NHWC [n,ho,wo,cout].  impl: 0 = CUDA-core fp32 kernel, 1 = tcgen05 3xTF32 kernel. */
+int fcp_conv2d(fcp_ctx* ctx, const float* x, int n, int h, int w, int cin, const float* weight, int cout, int k,
+               int stride, int pad, const float* scale, const float* shift, const float* residual, int act,
+               float slope, int impl, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FCP_B200_H */

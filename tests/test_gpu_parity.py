@@ -1,0 +1,287 @@
+"""GPU parity tests: every stage of the hot path, called through the C ABI (ctypes), against the CPU oracle
+and the reference-generated golden vectors.  Bars (BASELINE.json north_star): bit-exact NMS indices / anchor
+selection / warped pixels given identical inputs / parsing argmax given identical logits; <= 1e-3 max-abs on
+float32 landmarks, head outputs, logits and SR output."""
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+from face_crop_plus_b200 import synth
+from face_crop_plus_b200.landmarks import landmarks_target
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+CLASS_BIAS = 4.0          # the bias the golden vectors were generated with (tests/golden/meta.npz)
+TOL = 1e-3                # float32 tolerance stated by north_star
+
+
+def crc(a):
+    return zlib.crc32(np.ascontiguousarray(a).tobytes())
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from face_crop_plus_b200._abi import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def det_ctx(ctx):
+    from face_crop_plus_b200 import _abi
+    ctx.load_state_dict(_abi.MODEL_RETINAFACE, synth.make_state_dict("retinaface", 0, class_bias=CLASS_BIAS))
+    return ctx
+
+
+@pytest.fixture(scope="module")
+def par_ctx(ctx):
+    from face_crop_plus_b200 import _abi
+    ctx.load_state_dict(_abi.MODEL_BISENET, synth.make_state_dict("bisenet", 0))
+    return ctx
+
+
+@pytest.fixture(scope="module")
+def enh_ctx(ctx):
+    from face_crop_plus_b200 import _abi
+    ctx.load_state_dict(_abi.MODEL_RRDBNET, synth.make_state_dict("rrdbnet", 0))
+    return ctx
+
+
+# --------------------------------------------------------------------------------------------------- conv kernel
+CONV_CASES = [  # (n, h, w, cin, cout, k, stride, pad, act, residual)
+    (2, 17, 23, 64, 64, 3, 1, 1, "relu", False),
+    (1, 32, 32, 256, 128, 1, 1, 0, "none", True),
+    (2, 33, 31, 128, 256, 3, 2, 1, "relu", True),
+    (1, 16, 16, 512, 1024, 1, 2, 0, "none", False),
+    (1, 20, 24, 96, 32, 3, 1, 1, "lrelu", False),
+    (1, 64, 64, 256, 19, 1, 1, 0, "none", False),
+    (3, 9, 9, 32, 32, 1, 1, 0, "sigmoid", False),
+    (1, 40, 40, 192, 64, 3, 1, 1, "none", False),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("impl", [0])
+def test_conv2d_matches_torch(ctx, case, impl):
+    n, h, w, cin, cout, k, stride, pad, act, use_res = case
+    g = torch.Generator().manual_seed(hash(case) & 0xFFFF)
+    x = torch.randn((n, cin, h, w), generator=g)
+    wt = torch.randn((cout, cin, k, k), generator=g) * (2.0 / (cin * k * k)) ** 0.5
+    scale = 1 + 0.1 * torch.randn(cout, generator=g)
+    shift = 0.1 * torch.randn(cout, generator=g)
+    ref = torch.nn.functional.conv2d(x.double(), wt.double(), None, stride, pad) * scale.double().view(1, -1, 1, 1) \
+        + shift.double().view(1, -1, 1, 1)
+    res = torch.randn(ref.shape, generator=g) if use_res else None
+    if use_res:
+        ref = ref + res.double()
+    ref = {"relu": torch.relu, "none": lambda t: t, "lrelu": lambda t: torch.nn.functional.leaky_relu(t, 0.2),
+           "sigmoid": torch.sigmoid}[act](ref)
+    got = ctx.conv2d(x.permute(0, 2, 3, 1).contiguous().numpy(), wt.numpy(), stride, pad, scale.numpy(), shift.numpy(),
+                     None if res is None else res.permute(0, 2, 3, 1).contiguous().numpy(), act, 0.2, impl)
+    np.testing.assert_allclose(got, ref.permute(0, 2, 3, 1).numpy(), atol=2e-5, rtol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------------- align
+def test_align_bit_exact_vs_reference_crops(ctx, golden):
+    from oracle import align
+    g = golden["align"]
+    imgs = synth.make_images(2, 300, 260, seed=int(g["images_seed"]))
+    lms, idx, pads = g["landmarks"], g["indices"], g["paddings"]
+    tgt = landmarks_target((256, 256), 0.65)
+    for mode in align.BORDER_MODES:
+        for skew in (False, True):
+            crops, mats, valid = ctx.align(imgs, pads, idx, lms, tgt, (256, 256), mode, skew)
+            assert valid.all()
+            np.testing.assert_allclose(mats, g["matrices_affine" if skew else "matrices_partial"], atol=1e-8, rtol=0)
+            assert [crc(c) for c in crops] == g[f"crc_{mode}_{int(skew)}"].tolist(), (mode, skew)
+    crops, _, _ = ctx.align(imgs, None, idx, lms, landmarks_target((112, 160), 0.8), (112, 160))
+    assert np.array_equal(crops, g["crops_112x160"])
+
+
+def test_align_random_sizes_list_and_degenerate(ctx):
+    from oracle import align
+    rng = np.random.default_rng(5)
+    tgt = landmarks_target((256, 256), 0.65)
+    imgs, lms, idx = [], [], []
+    for i in range(6):
+        H, W = int(rng.integers(8, 500)), int(rng.integers(8, 500))
+        imgs.append(rng.integers(0, 256, (H, W, 3), dtype=np.uint8))
+        lms.append(synth.make_landmarks(1, max(min(H, W), 16), seed=70 + i)[0])
+        idx.append(i)
+    lms.append(np.full((5, 2), 3.0, np.float32))      # coincident points: no transform (cropper.py:529-531)
+    idx.append(0)
+    lms = np.stack(lms)
+    for mode in align.BORDER_MODES:
+        crops, mats, valid = ctx.align(imgs, None, idx, lms, tgt, (256, 256), mode)
+        ref, rmats, rvalid = align.crop_align(imgs, None, idx, lms, tgt, (256, 256), mode)
+        assert valid.tolist() == rvalid.tolist() == [True] * 6 + [False]
+        assert np.array_equal(crops[valid], ref), mode
+        np.testing.assert_allclose(mats[valid], rmats[rvalid], atol=1e-9, rtol=0)
+        assert not crops[~valid].any()
+    crops, mats, valid = ctx.align(imgs, None, [], np.zeros((0, 5, 2), np.float32), tgt)
+    assert crops.shape == (0, 256, 256, 3)
+
+
+def test_align_full_size_property(ctx):
+    # 1024x1024 source, 64 faces: identity-like transforms must reproduce the source window exactly
+    img = synth.make_images(1, 1024, 1024, seed=9)
+    tgt = landmarks_target((256, 256), 0.65)
+    shifts = np.array([[x, y] for x in range(0, 768, 96) for y in range(0, 768, 96)], np.float32)
+    lms = tgt[None] + shifts[:, None, :]              # pure integer translation -> crop == img[y:y+256, x:x+256]
+    crops, mats, valid = ctx.align(img, None, np.zeros(len(lms), np.int32), lms, tgt)
+    assert valid.all()
+    for (x, y), c in zip(shifts.astype(int), crops):
+        assert np.array_equal(c, img[0, y:y + 256, x:x + 256])
+
+
+# ------------------------------------------------------------------------------------------------- detection post
+@pytest.mark.parametrize("strategy", ["all", "best", "largest"])
+def test_detect_post_on_reference_heads(ctx, golden, strategy):
+    g = golden["detect"]
+    n, h, w, _ = (int(v) for v in g["shape"])
+    heads = np.concatenate([g["cls_raw"], g["boxes_raw"], g["ldms_raw"]], -1)
+    out = ctx.detect_post(heads, h, w, 0.6, 0.4, strategy)
+    assert out["indices"].tolist() == g[f"indices_{strategy}"].tolist()          # bit-exact selection
+    np.testing.assert_allclose(out["landmarks"], g[f"landmarks_{strategy}"], atol=1e-4, rtol=0)
+    out = ctx.detect_post(heads, h, w, 1.0, 0.4, strategy)                        # nothing passes -> empty
+    assert out["landmarks"].shape == (0, 5, 2) and len(out["indices"]) == 0
+
+
+def test_detect_post_clustered_nms_matches_oracle(ctx):
+    # dense clusters of overlapping boxes (many suppressions, > 4096 candidates on one image: exercises both sort paths)
+    from oracle import detpost
+    rng = np.random.default_rng(3)
+    h = w = 512
+    a = detpost.priors(h, w).shape[0]
+    heads = np.zeros((3, a, 16), np.float32)
+    heads[..., 0] = 4.0
+    heads[..., 1] = rng.normal(-2, 3, (3, a))
+    heads[1, :, 1] += 5                                                           # image 1: ~70% of priors pass
+    heads[..., 2:6] = rng.normal(0, 1.5, (3, a, 4))
+    heads[..., 6:] = rng.normal(0, 2, (3, a, 10))
+    for strategy in ("all", "best", "largest"):
+        l, i, anc, b = detpost.detect_post(heads[..., :2], heads[..., 2:6], heads[..., 6:], h, w, 0.6, 0.4, strategy)
+        out = ctx.detect_post(heads, h, w, 0.6, 0.4, strategy)
+        assert out["indices"].tolist() == i and out["anchors"].tolist() == anc
+        np.testing.assert_allclose(out["landmarks"], l, atol=1e-3, rtol=0)
+        np.testing.assert_allclose(out["boxes"], b, atol=1e-3, rtol=1e-6)
+    assert len(i) == 3
+
+
+def test_detect_post_capacity_error(ctx, golden):
+    from face_crop_plus_b200._abi import FcpError
+    g = golden["detect"]
+    n, h, w, _ = (int(v) for v in g["shape"])
+    heads = np.concatenate([g["cls_raw"], g["boxes_raw"], g["ldms_raw"]], -1)
+    out = ctx.detect_post(heads, h, w, 0.6, 0.4, "all", max_faces=4)              # wrapper grows the capacity
+    assert len(out["indices"]) == len(g["indices_all"])
+
+
+# ------------------------------------------------------------------------------------------------ detector network
+def test_detect_heads_match_reference(det_ctx, golden):
+    g = golden["detect"]
+    n, h, w, _ = (int(v) for v in g["shape"])
+    imgs = synth.make_images(n, h, w, seed=int(g["images_seed"]))
+    heads = det_ctx.detect_heads(imgs)
+    ref = np.concatenate([g["cls_raw"], g["boxes_raw"], g["ldms_raw"]], -1)
+    assert np.abs(heads - ref).max() < TOL, np.abs(heads - ref).max()
+
+
+@pytest.mark.parametrize("strategy", ["all", "best", "largest"])
+def test_detect_matches_reference_predict(det_ctx, golden, strategy):
+    g = golden["detect"]
+    n, h, w, _ = (int(v) for v in g["shape"])
+    imgs = synth.make_images(n, h, w, seed=int(g["images_seed"]))
+    det_ctx.set_micro_batch(2, 32)                     # 3 images -> micro-batches of 2 + 1 (ragged tail)
+    out = det_ctx.detect(imgs, 0.6, 0.4, strategy)
+    det_ctx.set_micro_batch(8, 32)
+    assert out["indices"].tolist() == g[f"indices_{strategy}"].tolist()
+    assert np.abs(out["landmarks"] - g[f"landmarks_{strategy}"]).max() < TOL
+
+
+def test_detect_device_input_and_no_faces(det_ctx):
+    imgs = synth.make_images(2, 256, 256, seed=31)
+    host = det_ctx.detect(imgs, 0.6, 0.4, "all")
+    dev = det_ctx.detect(torch.from_numpy(imgs).cuda(), 0.6, 0.4, "all")
+    assert host["indices"].tolist() == dev["indices"].tolist() and np.array_equal(host["landmarks"], dev["landmarks"])
+    none = det_ctx.detect(imgs, 1.0, 0.4, "largest")
+    assert none["landmarks"].shape == (0, 5, 2)
+
+
+# --------------------------------------------------------------------------------------------------------- parser
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_parse_tail_bit_exact_on_reference_logits(ctx, golden, tag):
+    g = golden["parse"]
+    n, h, w, _ = (int(v) for v in g[f"{tag}_shape"])
+    labels, hist = ctx.parse_tail(g[f"{tag}_logits64"], h, w)
+    assert np.array_equal(labels, g[f"{tag}_labels"])
+    assert np.array_equal(hist, np.stack([np.bincount(l.ravel(), minlength=19) for l in g[f"{tag}_labels"]]))
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_parse_matches_reference(par_ctx, golden, tag):
+    g = golden["parse"]
+    n, h, w, _ = (int(v) for v in g[f"{tag}_shape"])
+    crops = synth.make_images(n, h, w, seed=int(g[f"{tag}_seed"]))
+    logits = par_ctx.parse_logits(crops)
+    assert np.abs(logits - g[f"{tag}_logits64"]).max() < TOL
+    par_ctx.set_micro_batch(8, 2)                      # ragged face micro-batches
+    labels, hist = par_ctx.parse(crops)
+    par_ctx.set_micro_batch(8, 32)
+    diff = labels != g[f"{tag}_labels"]
+    if diff.any():   # argmax may flip only where the reference's own top-2 logits are within the float tolerance
+        ref_lg = torch.from_numpy(g[f"{tag}_logits64"])
+        up = torch.nn.functional.interpolate(torch.nn.functional.interpolate(ref_lg, (512, 512), None, "bilinear", True),
+                                             (h, w), mode="nearest")
+        top2 = up.topk(2, dim=1).values
+        margin = (top2[:, 0] - top2[:, 1]).numpy()
+        assert margin[diff].max() < 2 * TOL and diff.mean() < 1e-4
+    assert np.array_equal(hist, np.stack([np.bincount(l.ravel(), minlength=19) for l in labels]))
+
+
+def test_masks_and_grouping(ctx, golden):
+    g = golden["parse"]
+    labels = g["a_labels"]
+    for name, classes in {"eyes_and_eyebrows": [2, 3, 4, 5], "skin": [1], "lips": [11, 12, 13]}.items():
+        m = ctx.masks(labels, classes)
+        assert np.array_equal(m, (np.isin(labels, classes) * 255).astype(np.uint8))
+
+
+# ------------------------------------------------------------------------------------------------------- enhancer
+def test_enhance_matches_reference(enh_ctx, golden):
+    g = golden["enhance"]
+    x = torch.from_numpy(synth.make_images(2, 24, 32, seed=int(g["images_seed"]))).permute(0, 3, 1, 2).float()
+    y = enh_ctx.enhance_forward((x[:1] / 255).numpy())
+    assert np.abs(y - g["forward0"]).max() < TOL
+    imgs = x.clone().numpy()
+    out = enh_ctx.enhance(imgs, gate=[1, 0])
+    assert np.array_equal(out[1], x[1].numpy())                                    # gated off: untouched
+    d = np.abs(out[0] - g["predict"][0])
+    assert d.max() <= 1 and (d > 0).mean() < 0.01                                  # only x.5 rounding ties may flip
+    dev = x.clone().cuda()
+    enh_ctx.enhance(dev, gate=None)
+    assert np.abs(dev.cpu().numpy() - g["predict_all"]).max() <= 1
+
+
+# ----------------------------------------------------------------------------------------------------- whole path
+def test_pipeline_matches_oracle(det_ctx, par_ctx):
+    from oracle import pipeline
+    imgs = synth.make_images(3, 256, 320, seed=2000)
+    pads = np.array([[0, 0, 0, 0], [4, 2, 6, 0], [0, 0, 0, 0]], np.int32)
+    det_sd = synth.make_state_dict("retinaface", 0, class_bias=CLASS_BIAS)
+    par_sd = synth.make_state_dict("bisenet", 0)
+    tgt = landmarks_target((256, 256), 0.65)
+    for strategy in ("largest", "all"):
+        ref = pipeline.process_batch(imgs, det_sd, par_sd, paddings=pads, strategy=strategy, det_threshold=0.9)
+        out = det_ctx.pipeline(imgs, pads, tgt, (256, 256), 0.9, 0.4, strategy)
+        assert out["indices"].tolist() == ref["indices"]
+        assert np.abs(out["landmarks"] - ref["landmarks"]).max() < TOL
+        np.testing.assert_allclose(out["matrices"], ref["matrices"], atol=1e-4, rtol=0)
+        # crops: identical wherever the fixed-point source coordinates agree; landmark noise of ~1e-4 px can move a
+        # 1/32-px interpolation bin, so compare pixel values with a small tolerance and require near-total equality
+        d = np.abs(out["crops"].astype(int) - ref["crops"].astype(int))
+        assert (d > 0).mean() < 0.02 and d.max() <= 16
+        assert (out["labels"] != ref["labels"]).mean() < 5e-3
