@@ -35,6 +35,8 @@ SIGNATURES = {
     "fcp_launch_count": (C.c_int64, [_p]),
     "fcp_set_micro_batch": (_i, [_p, _i, _i]),
     "fcp_set_conv_impl": (_i, [_p, _i]),
+    "fcp_profile": (_i, [_p, _i]),
+    "fcp_profile_read": (_i, [_p, C.POINTER(C.c_double)]),
     "fcp_load_tensor": (_i, [_p, _i, C.c_char_p, _p, C.POINTER(C.c_int64), _i]),
     "fcp_finalize": (_i, [_p, _i, _i]),
     "fcp_detect": (_i, [_p, _p, _i, _i, _i, _f, _f, _i, _i, _p, _p, _p, _p, _p, _p]),
@@ -135,6 +137,14 @@ class Context:
 
     def set_conv_impl(self, impl: int):
         self.check(self.lib.fcp_set_conv_impl(self.h, impl))
+
+    def profile(self, enable: bool):
+        self.check(self.lib.fcp_profile(self.h, int(enable)))
+
+    def profile_read(self) -> dict:
+        out = (C.c_double * 4)()
+        self.check(self.lib.fcp_profile_read(self.h, out))
+        return dict(conv_ms=out[0], conv_launches=int(out[1]), conv_flops=out[2], conv_bytes=out[3])
 
     def load_state_dict(self, model: int, state_dict, rrdb_blocks: int = 23):
         """Feeds a reference-format state_dict (torch tensors or numpy arrays) and finalizes the model."""

@@ -108,6 +108,11 @@ struct fcp_ctx {
     void* pinned = nullptr; size_t pinned_bytes = 0;
     int sm_count = 148;
     int use_tc = 0;            // default conv implementation for the model graphs (0 ffma, 1 tcgen05)
+    // profiling (fcp_profile): event pairs around conv launches + algorithmic work counters
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_events;   // start0, stop0, start1, stop1, ...
+    size_t prof_used = 0;
+    double prof_flops = 0, prof_bytes = 0;
 };
 
 namespace fcp {

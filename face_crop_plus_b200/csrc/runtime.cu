@@ -213,7 +213,24 @@ DevOut::~DevOut() {
 }
 
 int run_conv(fcp_ctx* ctx, const ConvOp& op) {
-    return op.impl == 1 ? launch_conv_tc(ctx, op) : launch_conv_ffma(ctx, op);
+    if (!ctx->profile) return op.impl == 1 ? launch_conv_tc(ctx, op) : launch_conv_ffma(ctx, op);
+    if (ctx->prof_used + 2 > ctx->prof_events.size()) {
+        cudaEvent_t a, b;
+        FCP_CUDA(ctx, cudaEventCreate(&a));
+        FCP_CUDA(ctx, cudaEventCreate(&b));
+        ctx->prof_events.push_back(a);
+        ctx->prof_events.push_back(b);
+    }
+    cudaEvent_t e0 = ctx->prof_events[ctx->prof_used], e1 = ctx->prof_events[ctx->prof_used + 1];
+    ctx->prof_used += 2;
+    FCP_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+    int s = op.impl == 1 ? launch_conv_tc(ctx, op) : launch_conv_ffma(ctx, op);
+    FCP_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+    const ConvWeights& w = *op.wt;
+    const double M = (double)op.out.n * op.out.h * op.out.w, K = (double)w.k * w.k * w.cin;
+    ctx->prof_flops += 2.0 * M * w.cout * K;
+    ctx->prof_bytes += 4.0 * ((double)op.in.pixels() * w.cin + M * w.cout + K * w.cout);
+    return s;
 }
 
 }  // namespace fcp
@@ -255,6 +272,7 @@ void fcp_destroy(fcp_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (void* p : ctx->device_allocs) cudaFree(p);
+    for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -290,6 +308,26 @@ int fcp_set_micro_batch(fcp_ctx* ctx, int detect_images, int parse_faces) {
 int fcp_set_conv_impl(fcp_ctx* ctx, int impl) {
     if (!ctx || impl < 0 || impl > 1) return fail(ctx, FCP_ERR_INVALID, "conv impl must be 0 or 1");
     ctx->use_tc = impl;
+    return FCP_OK;
+}
+
+int fcp_profile(fcp_ctx* ctx, int enable) {
+    if (!ctx) return FCP_ERR_INVALID;
+    ctx->profile = enable != 0;
+    return FCP_OK;
+}
+
+int fcp_profile_read(fcp_ctx* ctx, double* out4) {
+    if (!ctx || !out4) return fail(ctx, FCP_ERR_INVALID, "fcp_profile_read: bad argument");
+    FCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double ms = 0;
+    for (size_t i = 0; i + 1 < ctx->prof_used; i += 2) {
+        float t = 0;
+        FCP_CUDA(ctx, cudaEventElapsedTime(&t, ctx->prof_events[i], ctx->prof_events[i + 1]));
+        ms += t;
+    }
+    out4[0] = ms; out4[1] = (double)(ctx->prof_used / 2); out4[2] = ctx->prof_flops; out4[3] = ctx->prof_bytes;
+    ctx->prof_used = 0; ctx->prof_flops = 0; ctx->prof_bytes = 0;
     return FCP_OK;
 }
 

@@ -58,6 +58,13 @@ int fcp_set_micro_batch(fcp_ctx* ctx, int detect_images, int parse_faces);
 /* convolution kernel used by the model graphs: 0 = CUDA-core fp32, 1 = tcgen05 3xTF32 (same results to fp32 rounding) */
 int fcp_set_conv_impl(fcp_ctx* ctx, int impl);
 
+/* per-kernel timing for bench.py's roofline line: when enabled, every convolution launch is bracketed by CUDA events
+ * on the context stream.  fcp_profile_read synchronizes and returns, accumulated since the last read:
+ * out[0] = convolution kernel time (ms), out[1] = convolution launches, out[2] = algorithmic convolution FLOPs
+ * (2*M*Cout*K of the true, un-padded shapes), out[3] = algorithmic bytes (activations in+out, weights once per launch) */
+int fcp_profile(fcp_ctx* ctx, int enable);
+int fcp_profile_read(fcp_ctx* ctx, double* out4);
+
 /* ---- weights: replaces LoadMixin.load / get_weights (models/_layers.py:16-35) ---------------------------
  * Feed every entry of the reference state_dict (same keys, float32, host memory, OIHW conv weights), then
  * finalize: BN running stats are folded into per-channel scale/shift, conv weights are re-packed for the

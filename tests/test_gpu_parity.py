@@ -253,7 +253,7 @@ def test_masks_and_grouping(ctx, golden):
 # ------------------------------------------------------------------------------------------------------- enhancer
 def test_enhance_matches_reference(enh_ctx, golden):
     g = golden["enhance"]
-    x = torch.from_numpy(synth.make_images(2, 24, 32, seed=int(g["images_seed"]))).permute(0, 3, 1, 2).float()
+    x = torch.from_numpy(synth.make_images(2, 24, 32, seed=int(g["images_seed"]))).permute(0, 3, 1, 2).float().contiguous()
     y = enh_ctx.enhance_forward((x[:1] / 255).numpy())
     assert np.abs(y - g["forward0"]).max() < TOL
     imgs = x.clone().numpy()
@@ -279,7 +279,8 @@ def test_pipeline_matches_oracle(det_ctx, par_ctx):
         out = det_ctx.pipeline(imgs, pads, tgt, (256, 256), 0.9, 0.4, strategy)
         assert out["indices"].tolist() == ref["indices"]
         assert np.abs(out["landmarks"] - ref["landmarks"]).max() < TOL
-        np.testing.assert_allclose(out["matrices"], ref["matrices"], atol=1e-4, rtol=0)
+        # landmark noise (<= TOL px) is amplified by the source coordinates (~|M| * 320 px) in the translation column
+        np.testing.assert_allclose(out["matrices"], ref["matrices"], atol=5e-3, rtol=0)
         # crops: identical wherever the fixed-point source coordinates agree; landmark noise of ~1e-4 px can move a
         # 1/32-px interpolation bin, so compare pixel values with a small tolerance and require near-total equality
         d = np.abs(out["crops"].astype(int) - ref["crops"].astype(int))
