@@ -1,0 +1,46 @@
+"""CPU: host-side logic of the drop-in mirror that needs no GPU."""
+import numpy as np
+import pytest
+
+from face_crop_plus_b200 import synth, utils
+from face_crop_plus_b200.landmarks import landmarks_target
+
+
+def test_landmark_slices():
+    assert [(s.start, s.stop) for s in utils.get_ldm_slices(5, 68)] == [(36, 42), (42, 48), (30, 31), (48, 49), (54, 55)]
+    with pytest.raises(ValueError):
+        utils.get_ldm_slices(5, 7)
+    with pytest.raises(ValueError):
+        utils.get_ldm_slices(4, 68)
+    with pytest.raises(ValueError):
+        landmarks_target((256, 256), 0.65, 4)
+
+
+def test_as_batch_geometry():
+    pytest.importorskip("cv2")
+    imgs = [np.zeros((100, 200, 3), np.uint8), np.zeros((300, 150, 3), np.uint8), np.zeros((64, 64, 3), np.uint8)]
+    batch, unscales, pads = utils.as_batch(imgs, (128, 96))
+    assert batch.shape == (3, 96, 128, 3)
+    assert pads.tolist() == [[16, 16, 0, 0], [0, 0, 40, 40], [0, 0, 16, 16]]
+    np.testing.assert_allclose(unscales, [0.64, 0.32, 1.5])
+    same, _, pads = utils.as_batch([synth.make_images(1, 64, 64)[0]], 64)       # identity at the native size
+    assert np.array_equal(same[0], synth.make_images(1, 64, 64)[0]) and not pads.any()
+
+
+def test_enhance_gate_matches_oracle():
+    from face_crop_plus_b200.models import RRDBNet
+    from oracle import enhance
+    rng = np.random.default_rng(0)
+    lms = rng.uniform(0, 64, (7, 5, 2)).astype(np.float32)
+    idx = [0, 0, 1, 3, 3, 3, 4]
+    m = RRDBNet(0.05)
+    g = m.gate(6, 64, 80, lms, idx)
+    assert g.tolist() == [int(enhance.should_enhance(lms, idx, i, 64, 80, 0.05)) for i in range(6)]
+    assert m.gate(3, 64, 80, None, None).tolist() == [1, 1, 1]
+
+
+def test_parse_landmarks_file(tmp_path):
+    p = tmp_path / "l.txt"
+    p.write_text("a.jpg 1 2 3 4 5 6 7 8 9 10\nb.jpg 10 9 8 7 6 5 4 3 2 1\n")
+    lms, names = utils.parse_landmarks_file(str(p))
+    assert lms.shape == (2, 5, 2) and names.tolist() == ["a.jpg", "b.jpg"] and lms[1, 0].tolist() == [10, 9]
