@@ -43,7 +43,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         list(pool.map(run, jobs))
     objs = [str(objdir / (n + ".o")) for n in SOURCES]
     if jobs or not LIB.exists():
-        run([NVCC, "-shared", "-o", str(LIB), *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-lcuda"])
+        run([NVCC, "-shared", "-o", str(LIB), *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"])
     return LIB
 
 

@@ -143,6 +143,7 @@ int fail(fcp_ctx* ctx, int code, const std::string& msg);
 // ---- kernels (one launcher per .cu) -----------------------------------------------------------------------
 int launch_conv_ffma(fcp_ctx* ctx, const ConvOp& op);
 int launch_conv_tc(fcp_ctx* ctx, const ConvOp& op);
+bool conv_tc_supported(const ConvOp& op);
 int run_conv(fcp_ctx* ctx, const ConvOp& op);
 
 // stem: 7x7/s2 conv (Cin=3 -> 64) + scale/shift + ReLU.  mode 0: src = u8 RGB NHWC, flipped to BGR and mean-subtracted

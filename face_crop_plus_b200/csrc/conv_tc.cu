@@ -1,5 +1,453 @@
-// conv_tc.cu — tcgen05 / TMA implicit-GEMM convolution (3xTF32 split).  Placeholder until the kernel lands.
+// conv_tc.cu — implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM), operands
+// staged by TMA, fp32-equivalent through a 3xTF32 split.  sm_100a only.
+//
+// Replaces the same nn.Conv2d(+BN+act+residual) sites as conv_ffma.cu; same ConvOp contract and epilogue.
+//
+// GEMM view: D[M = N*Ho*Wo pixels, Cout] = A[M, K = KH*KW*Cin] * W[Cout, K]^T, NHWC activations (K-major rows of 32
+// channels = 128 B), weights pre-packed K-major.  No im2col buffer exists anywhere: for every (tap, 32-channel) K-block
+// the TMA engine loads the *shifted* BHxBW spatial box of the input straight into the 128B-swizzled K-major tile the
+// MMA descriptor expects; out-of-image rows/columns are zero-filled by TMA (== the conv's zero padding).  Stride-2
+// convolutions address one of four parity views of the input (x = 2i+p), so their boxes are dense as well.
+//
+// Precision (parity bar: landmarks <= 1e-3 px, bit-exact argmax => single-pass TF32/BF16 is not enough):
+//   a = a_hi + a_lo, w = w_hi + w_lo with *_hi = value truncated to TF32;  D += a_hi*w_hi + a_lo*w_hi + a_hi*w_lo.
+//   w_hi/w_lo are split on the host; a_hi/a_lo are split on the fly by 4 converter warps working in shared memory
+//   (elementwise, so the swizzled layout is preserved).  Every operand has its low 13 mantissa bits zeroed, hence the
+//   result does not depend on how the tensor core rounds fp32 -> tf32.
+//
+//   Measured on B200: the TMEM accumulator add rounds toward zero (~3e-8 relative loss per accumulate, 5e-5 over a
+//   K=4608 chain) - a systematic shrink that a 60-layer network amplifies.  Therefore a TMEM accumulation chain never
+//   spans more than ONE K-block: the 8 small-term MMAs (a_lo*w_hi, a_hi*w_lo) go first, the 4 a_hi*w_hi MMAs last, then
+//   the block's partial sum is drained to fp32 registers and added there with round-to-nearest.
+//
+// CTA = 14 warps, persistent over output tiles (128 pixels x BN channels):
+//   warp 0      TMA producer          full[s]  <- TMA bytes          (waits empty[s])
+//   warps 2-5   hi/lo converters      conv[s]  <- 128 arrivals       (wait full[s])
+//   warp 1      MMA issuer (1 lane)   empty[s], d_full[b] <- tcgen05.commit     (waits conv[s], d_empty[b])
+//   warps 6-13  accumulate+epilogue   d_empty[b] <- 256 arrivals     (wait d_full[b]); per K-block TMEM -> regs (+=),
+//               after the last K-block: fused epilogue -> HBM.  Warp w owns TMEM lanes 32*(w%4).. and half of the columns.
+// Two TMEM partial-sum buffers let the drain of K-block i overlap the MMAs of K-block i+1.
+#include <cuda.h>
+
 #include "common.h"
+
 namespace fcp {
-int launch_conv_tc(fcp_ctx* ctx, const ConvOp&) { return fail(ctx, FCP_ERR_INVALID, "tcgen05 conv kernel not built"); }
+
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int KB = 32;                         // channels per K-block (128 bytes of fp32)
+constexpr int A_TILE_BYTES = TILE_M * KB * 4;  // 16 KiB
+constexpr int NUM_THREADS = 448;
+
+struct alignas(64) TcParams {
+    CUtensorMap tmA[4];                        // input, one per (row parity, column parity); stride 1 uses [0]
+    CUtensorMap tmBhi, tmBlo;                  // weights [cout_pad][K], K-major
+    int N, Ho, Wo, Cout, Cin, KH, KW, stride, pad;
+    int tiles_x, tiles_y, tiles_n, num_tiles, bw_log2, BH;
+    float* out; int out_cs, out_co;
+    const float* scale; const float* shift;
+    const float* res1; int res1_cs, res1_co;
+    int act; float slope;
+    float post_scale; const float* res2; int res2_cs, res2_co, res2_h, res2_w;
+    float post_scale2; const float* res3; int res3_cs, res3_co;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    const uint32_t addr = smem_u32(bar);
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, one CTA
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives on `bar` when all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x N consecutive 32-bit columns: thread i of the warp receives lane (base_lane + i)
+template <int N> __device__ __forceinline__ void tmem_ld(uint32_t taddr, float* v);
+template <> __device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <> __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row atoms 1024 bytes apart (SBO), LBO unused (=1),
+// descriptor version 1 (Blackwell), layout type 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+
+__device__ __forceinline__ float act_fn(float v, int act, float slope) {
+    if (act == FCP_ACT_RELU) return fmaxf(v, 0.f);
+    if (act == FCP_ACT_LRELU) return v > 0.f ? v : v * slope;
+    if (act == FCP_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+    return v;
+}
+
+template <int BN> struct Cfg {
+    static constexpr int B_TILE_BYTES = BN * KB * 4;
+    static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+    static constexpr int STAGES = BN >= 128 ? 3 : (BN == 64 ? 4 : 5);
+    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;           // 64, 128, 256 (powers of two)
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+    using C = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t* full = bars;                         // [STAGES]
+    uint64_t* conv = bars + C::STAGES;             // [STAGES]
+    uint64_t* empty = bars + 2 * C::STAGES;        // [STAGES]
+    uint64_t* d_full = bars + 3 * C::STAGES;       // [2]  partial sum of one K-block is complete in TMEM buffer b
+    uint64_t* d_empty = d_full + 2;                // [2]  buffer b has been drained to registers
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(d_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    auto stage_a_hi = [&](int s) { return smem + s * C::STAGE_BYTES; };
+    auto stage_a_lo = [&](int s) { return smem + s * C::STAGE_BYTES + A_TILE_BYTES; };
+    auto stage_b_hi = [&](int s) { return smem + s * C::STAGE_BYTES + 2 * A_TILE_BYTES; };
+    auto stage_b_lo = [&](int s) { return smem + s * C::STAGE_BYTES + 2 * A_TILE_BYTES + C::B_TILE_BYTES; };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&conv[s], 128); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&d_full[a], 1); mbar_init(&d_empty[a], 256); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_base_smem, C::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+
+    const int cchunks = p.Cin / KB;
+    const int kblocks = p.KH * p.KW * cchunks;
+    const int BW = 1 << p.bw_log2;
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+    if (warp == 0) {
+        // ================================================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
+                const int img = m_tile / tiles_per_img, rem = m_tile - img * tiles_per_img;
+                const int ho0 = (rem / p.tiles_x) * p.BH, wo0 = (rem % p.tiles_x) * BW;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    const int tap = kb / cchunks, c0 = (kb - tap * cchunks) * KB;
+                    const int r = tap / p.KW, s = tap - r * p.KW;
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], A_TILE_BYTES + 2 * C::B_TILE_BYTES);
+                    int dy = r - p.pad, dx = s - p.pad, map = 0;
+                    if (p.stride == 2) {   // input row 2*ho + dy lives in parity view (dy & 1) at row ho + (dy - (dy & 1)) / 2
+                        const int py = dy & 1, px = dx & 1;
+                        map = py * 2 + px;
+                        dy = (dy - py) >> 1;
+                        dx = (dx - px) >> 1;
+                    }
+                    tma_load_4d(stage_a_hi(stage), &p.tmA[map], &full[stage], c0, wo0 + dx, ho0 + dy, img);
+                    tma_load_2d(stage_b_hi(stage), &p.tmBhi, &full[stage], tap * p.Cin + c0, n_tile * BN);
+                    tma_load_2d(stage_b_lo(stage), &p.tmBlo, &full[stage], tap * p.Cin + c0, n_tile * BN);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ==================================================================================== MMA issuer
+        if (lane == 0) {
+            // instruction descriptor: D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10), both K-major, N>>3 at bit 17, M>>4 at bit 24
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+            int stage = 0; uint32_t phase = 0;
+            uint32_t g = 0;                                                   // K-blocks issued so far (all tiles)
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                for (int kb = 0; kb < kblocks; ++kb, ++g) {
+                    const uint32_t buf = g & 1;
+                    mbar_wait(&d_empty[buf], ((g >> 1) & 1) ^ 1);             // partial-sum buffer drained
+                    mbar_wait(&conv[stage], phase);                           // operands (hi/lo) ready in smem
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + buf * BN;
+                    const uint64_t a_hi = umma_desc(smem_u32(stage_a_hi(stage))), a_lo = umma_desc(smem_u32(stage_a_lo(stage)));
+                    const uint64_t b_hi = umma_desc(smem_u32(stage_b_hi(stage))), b_lo = umma_desc(smem_u32(stage_b_lo(stage)));
+                    // 8 tf32 = 32 bytes along K inside the 128-byte swizzle span -> +2 in the (addr >> 4) field per K-step.
+                    // Small terms first: while the accumulator is tiny its round-toward-zero losses are negligible.
+#pragma unroll
+                    for (int k = 0; k < KB / 8; ++k) {
+                        umma_tf32(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, k != 0);
+                        umma_tf32(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
+                    }
+#pragma unroll
+                    for (int k = 0; k < KB / 8; ++k) umma_tf32(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, 1);
+                    umma_commit(&empty[stage]);                               // smem slot reusable once these MMAs retire
+                    umma_commit(&d_full[buf]);                                // partial sum of this K-block complete
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp < 6) {
+        // ================================================================= hi/lo converters (warps 2..5, 128 threads)
+        const int t = threadIdx.x - 64;
+        const int chunk = t & 7, row0 = t >> 3;                               // 16-byte chunk of row (row0 + 16*i)
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&full[stage], phase);
+                uint8_t* hi = stage_a_hi(stage);
+                uint8_t* lo = stage_a_lo(stage);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int off = (row0 + 16 * i) * 128 + chunk * 16;
+                    uint4 v = *reinterpret_cast<uint4*>(hi + off);
+                    uint4 h, l;
+                    h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
+                    l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x)) & 0xFFFFE000u;
+                    l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y)) & 0xFFFFE000u;
+                    l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z)) & 0xFFFFE000u;
+                    l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w)) & 0xFFFFE000u;
+                    *reinterpret_cast<uint4*>(hi + off) = h;
+                    *reinterpret_cast<uint4*>(lo + off) = l;
+                }
+                fence_async_smem();                                           // generic-proxy writes -> visible to the MMA (async proxy)
+                mbar_arrive(&conv[stage]);
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ============================================================ accumulate + epilogue (warps 6..13, 256 threads)
+        constexpr int HALF = BN / 2;                                          // columns owned by this warp
+        constexpr int CH = HALF >= 32 ? 32 : 16;                              // columns per tcgen05.ld
+        constexpr int NCH = HALF / CH;
+        const int quarter = warp & 3;                                         // TMEM lanes [32*quarter, 32*quarter+32)
+        const int half = (warp - 6) >> 2;
+        const int pix = quarter * 32 + lane;                                  // row of the tile == pixel of the box
+        const uint32_t lane_col = ((uint32_t)(quarter * 32) << 16) + half * HALF;
+        uint32_t g = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            float acc[HALF];
+#pragma unroll
+            for (int j = 0; j < HALF; ++j) acc[j] = 0.f;
+            for (int kb = 0; kb < kblocks; ++kb, ++g) {
+                const uint32_t buf = g & 1;
+                mbar_wait(&d_full[buf], (g >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int cb = 0; cb < NCH; ++cb) {
+                    float v[CH];
+                    tmem_ld<CH>(tmem_base + buf * BN + lane_col + cb * CH, v);
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) acc[cb * CH + j] += v[j];     // round-to-nearest fp32 running sum
+                }
+                tc_fence_before();
+                mbar_arrive(&d_empty[buf]);
+            }
+            const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
+            const int img = m_tile / tiles_per_img, rem = m_tile - img * tiles_per_img;
+            const int ho = (rem / p.tiles_x) * p.BH + (pix >> p.bw_log2), wo = (rem % p.tiles_x) * BW + (pix & (BW - 1));
+            if (ho >= p.Ho || wo >= p.Wo) continue;
+            const size_t m = ((size_t)img * p.Ho + ho) * p.Wo + wo;
+            size_t res2_pix = m;
+            if (p.res2 && p.res2_h) {
+                int hs = min((int)floorf(ho * ((float)p.res2_h / (float)p.Ho)), p.res2_h - 1);
+                int ws = min((int)floorf(wo * ((float)p.res2_w / (float)p.Wo)), p.res2_w - 1);
+                res2_pix = ((size_t)img * p.res2_h + hs) * p.res2_w + ws;
+            }
+            const int n0 = n_tile * BN + half * HALF;
+#pragma unroll
+            for (int j = 0; j < HALF; ++j) {
+                const int n = n0 + j;
+                if (n < p.Cout) {
+                    float x = acc[j] * __ldg(p.scale + n) + __ldg(p.shift + n);
+                    if (p.res1) x += p.res1[m * p.res1_cs + p.res1_co + n];
+                    x = act_fn(x, p.act, p.slope);
+                    if (p.post_scale != 1.f) x *= p.post_scale;
+                    if (p.res2) x += p.res2[res2_pix * p.res2_cs + p.res2_co + n];
+                    if (p.post_scale2 != 1.f) x *= p.post_scale2;
+                    if (p.res3) x += p.res3[m * p.res3_cs + p.res3_co + n];
+                    acc[j] = x;
+                }
+            }
+            float* dst = p.out + m * p.out_cs + p.out_co + n0;
+#pragma unroll
+            for (int j = 0; j < HALF; j += 4) {
+                if (n0 + j + 3 < p.Cout) {
+                    *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                } else {
+                    if (n0 + j < p.Cout) dst[j] = acc[j];
+                    if (n0 + j + 1 < p.Cout) dst[j + 1] = acc[j + 1];
+                    if (n0 + j + 2 < p.Cout) dst[j + 2] = acc[j + 2];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// ----------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+bool make_map(CUtensorMap* map, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, base, dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN>
+int launch(fcp_ctx* ctx, const TcParams& p) {
+    using C = Cfg<BN>;
+    static bool configured = false;
+    if (!configured) {
+        FCP_CUDA(ctx, cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        configured = true;
+    }
+    int grid = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
+    conv_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, ctx->stream>>>(p);
+    FCP_KERNEL_CHECK(ctx);
+    return FCP_OK;
+}
+
+}  // namespace
+
+bool conv_tc_supported(const ConvOp& op) {
+    const ConvWeights& wt = *op.wt;
+    if (wt.cin % KB != 0 || op.up_in) return false;
+    if (op.stride != 1 && op.stride != 2) return false;
+    if (op.stride == 2 && !(wt.k == 1 || wt.k == 3)) return false;
+    if ((op.in.cs | op.in.co) & 3) return false;
+    if ((size_t)op.out.h * op.out.w < 64) return false;       // pooled 1x1 maps etc. stay on the CUDA-core kernel
+    return encode_fn() != nullptr;
+}
+
+int launch_conv_tc(fcp_ctx* ctx, const ConvOp& op) {
+    const ConvWeights& wt = *op.wt;
+    if (!conv_tc_supported(op)) return fail(ctx, FCP_ERR_INVALID, "conv_tc: unsupported shape");
+    if (op.in.c != wt.cin || op.out.c != wt.cout) return fail(ctx, FCP_ERR_INVALID, "conv: channel mismatch");
+    TcParams p{};
+    const int H = op.in.h, W = op.in.w, cs = op.in.cs;
+    p.N = op.in.n; p.Ho = op.out.h; p.Wo = op.out.w; p.Cout = wt.cout; p.Cin = wt.cin;
+    p.KH = p.KW = wt.k; p.stride = op.stride; p.pad = op.pad;
+    if ((H + 2 * op.pad - wt.k) / op.stride + 1 != p.Ho || (W + 2 * op.pad - wt.k) / op.stride + 1 != p.Wo)
+        return fail(ctx, FCP_ERR_INVALID, "conv: output shape mismatch");
+    // spatial box of 128 output pixels: widest power-of-two width that does not overshoot the row by more than 2x
+    int bw_log2 = 7;
+    while (bw_log2 > 0 && (1 << bw_log2) >= 2 * p.Wo) --bw_log2;
+    if (bw_log2 < 3) bw_log2 = 3;
+    int best = -1; size_t best_tiles = 0;
+    for (int l = 3; l <= 7; ++l) {                            // pick the box with the fewest tiles (ties: squarer)
+        int bw = 1 << l, bh = TILE_M / bw;
+        size_t t = (size_t)((p.Wo + bw - 1) / bw) * ((p.Ho + bh - 1) / bh);
+        if (best < 0 || t < best_tiles || (t == best_tiles && abs(l - 4) < abs(best - 4))) { best = l; best_tiles = t; }
+    }
+    bw_log2 = best;
+    const int BW = 1 << bw_log2, BH = TILE_M / BW;
+    p.bw_log2 = bw_log2; p.BH = BH;
+    p.tiles_x = (p.Wo + BW - 1) / BW; p.tiles_y = (p.Ho + BH - 1) / BH;
+    const int BN = wt.cout_pad % 128 == 0 ? 128 : (wt.cout_pad % 64 == 0 ? 64 : 32);
+    p.tiles_n = wt.cout_pad / BN;
+    p.num_tiles = p.N * p.tiles_x * p.tiles_y * p.tiles_n;
+    // ---- tensor maps
+    float* base = op.in.p + op.in.co;
+    const int nviews = op.stride == 2 ? 4 : 1;
+    for (int v = 0; v < nviews; ++v) {
+        const int py = v >> 1, px = v & 1, st = op.stride;
+        cuuint64_t dims[4] = {(cuuint64_t)wt.cin, (cuuint64_t)((W - px + st - 1) / st), (cuuint64_t)((H - py + st - 1) / st), (cuuint64_t)p.N};
+        cuuint64_t strides[3] = {(cuuint64_t)st * cs * 4, (cuuint64_t)st * W * cs * 4, (cuuint64_t)H * W * cs * 4};
+        cuuint32_t box[4] = {KB, (cuuint32_t)BW, (cuuint32_t)BH, 1};
+        if (dims[1] == 0 || dims[2] == 0) { dims[1] = dims[1] ? dims[1] : 1; dims[2] = dims[2] ? dims[2] : 1; }
+        if (!make_map(&p.tmA[v], base + ((size_t)py * W + px) * cs, 4, dims, strides, box))
+            return fail(ctx, FCP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the activation tensor");
+    }
+    const cuuint64_t K = (cuuint64_t)wt.k * wt.k * wt.cin;
+    cuuint64_t bdims[2] = {K, (cuuint64_t)wt.cout_pad};
+    cuuint64_t bstr[1] = {K * 4};
+    cuuint32_t bbox[2] = {KB, (cuuint32_t)BN};
+    if (!make_map(&p.tmBhi, wt.w_hi, 2, bdims, bstr, bbox) || !make_map(&p.tmBlo, wt.w_lo, 2, bdims, bstr, bbox))
+        return fail(ctx, FCP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the weights");
+    p.out = op.out.p; p.out_cs = op.out.cs; p.out_co = op.out.co;
+    p.scale = wt.scale; p.shift = wt.shift;
+    p.res1 = op.res1; p.res1_cs = op.res1_cs; p.res1_co = op.res1_co;
+    p.act = op.act; p.slope = op.slope;
+    p.post_scale = op.post_scale; p.res2 = op.res2; p.res2_cs = op.res2_cs; p.res2_co = op.res2_co; p.res2_h = op.res2_h; p.res2_w = op.res2_w;
+    p.post_scale2 = op.post_scale2; p.res3 = op.res3; p.res3_cs = op.res3_cs; p.res3_co = op.res3_co;
+    if (BN == 128) return launch<128>(ctx, p);
+    if (BN == 64) return launch<64>(ctx, p);
+    return launch<32>(ctx, p);
+}
+
 }  // namespace fcp

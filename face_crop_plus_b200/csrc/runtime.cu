@@ -140,7 +140,7 @@ int pack_conv(fcp_ctx* ctx, Model& m, const std::vector<std::string>& convs, con
                         wkn[kk * cw.cout_pad + o0 + o] = v;
                         float hi = tf32_trunc(v);
                         whi[(size_t)(o0 + o) * K + kk] = hi;
-                        wlo[(size_t)(o0 + o) * K + kk] = v - hi;
+                        wlo[(size_t)(o0 + o) * K + kk] = tf32_trunc(v - hi);
                     }
         if (bs[g])
             for (int o = 0; o < co_n; ++o) shift[o0 + o] = bs[g]->data[o];
@@ -213,7 +213,8 @@ DevOut::~DevOut() {
 }
 
 int run_conv(fcp_ctx* ctx, const ConvOp& op) {
-    if (!ctx->profile) return op.impl == 1 ? launch_conv_tc(ctx, op) : launch_conv_ffma(ctx, op);
+    const bool tc = op.impl == 1 && conv_tc_supported(op);   // shapes the tensor-core kernel does not cover use the CUDA-core kernel
+    if (!ctx->profile) return tc ? launch_conv_tc(ctx, op) : launch_conv_ffma(ctx, op);
     if (ctx->prof_used + 2 > ctx->prof_events.size()) {
         cudaEvent_t a, b;
         FCP_CUDA(ctx, cudaEventCreate(&a));
@@ -224,7 +225,7 @@ int run_conv(fcp_ctx* ctx, const ConvOp& op) {
     cudaEvent_t e0 = ctx->prof_events[ctx->prof_used], e1 = ctx->prof_events[ctx->prof_used + 1];
     ctx->prof_used += 2;
     FCP_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
-    int s = op.impl == 1 ? launch_conv_tc(ctx, op) : launch_conv_ffma(ctx, op);
+    int s = tc ? launch_conv_tc(ctx, op) : launch_conv_ffma(ctx, op);
     FCP_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
     const ConvWeights& w = *op.wt;
     const double M = (double)op.out.n * op.out.h * op.out.w, K = (double)w.k * w.k * w.cin;

@@ -64,7 +64,7 @@ CONV_CASES = [  # (n, h, w, cin, cout, k, stride, pad, act, residual)
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
-@pytest.mark.parametrize("impl", [0])
+@pytest.mark.parametrize("impl", [0, 1])
 def test_conv2d_matches_torch(ctx, case, impl):
     n, h, w, cin, cout, k, stride, pad, act, use_res = case
     g = torch.Generator().manual_seed(hash(case) & 0xFFFF)
@@ -82,6 +82,22 @@ def test_conv2d_matches_torch(ctx, case, impl):
     got = ctx.conv2d(x.permute(0, 2, 3, 1).contiguous().numpy(), wt.numpy(), stride, pad, scale.numpy(), shift.numpy(),
                      None if res is None else res.permute(0, 2, 3, 1).contiguous().numpy(), act, 0.2, impl)
     np.testing.assert_allclose(got, ref.permute(0, 2, 3, 1).numpy(), atol=2e-5, rtol=1e-5)
+
+
+def test_conv2d_tensor_core_accuracy_large_k(ctx):
+    """3xTF32 on tcgen05 must be as accurate as the fp32 CUDA-core kernel (K = 9*512 = 4608, fp64 reference)."""
+    g = torch.Generator().manual_seed(7)
+    n, h, w, cin, cout = 2, 32, 32, 512, 256
+    x = torch.randn((n, cin, h, w), generator=g).abs() + 0.5           # all-positive inputs: worst case for biased rounding
+    wt = torch.randn((cout, cin, 3, 3), generator=g) * (2.0 / (cin * 9)) ** 0.5 + 0.01
+    ref = torch.nn.functional.conv2d(x.double(), wt.double(), None, 1, 1).permute(0, 2, 3, 1).numpy()
+    xin = x.permute(0, 2, 3, 1).contiguous().numpy()
+    err = {}
+    for impl in (0, 1):
+        got = ctx.conv2d(xin, wt.numpy(), 1, 1, impl=impl)
+        err[impl] = np.abs(got - ref).max() / np.abs(ref).max()
+    print("relative max error  cuda-core fp32: %.3e   tcgen05 3xTF32: %.3e" % (err[0], err[1]))
+    assert err[1] < 5e-6 and err[1] < 8 * max(err[0], 1e-7)
 
 
 # ---------------------------------------------------------------------------------------------------------- align
