@@ -43,9 +43,9 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--size", type=int, default=1024)
     ap.add_argument("--class-bias", type=float, default=4.8)
-    ap.add_argument("--det-mb", type=int, default=8)
+    ap.add_argument("--det-mb", type=int, default=16)
     ap.add_argument("--par-mb", type=int, default=32)
-    ap.add_argument("--conv-impl", type=int, default=int(os.environ.get("FCP_CONV_IMPL", "0")))
+    ap.add_argument("--conv-impl", type=int, default=int(os.environ.get("FCP_CONV_IMPL", "1")))
     ap.add_argument("--cpu-sample", type=int, default=4, help="images in the cpu_baseline sample (0 = skip)")
     return ap.parse_args()
 
@@ -184,20 +184,18 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                     labels=torch.zeros((cap, 256, 256), dtype=torch.uint8, **kw), hist=torch.zeros((cap, 19), dtype=torch.int32, **kw))
 
     dev_out, host_out = outputs(dev), outputs(None)
-    meta = torch.zeros((cap, 24), dtype=torch.float32, device=dev)            # per-face record for the all-gather
-    gathered = torch.zeros((world * cap, 24), dtype=torch.float32, device=dev) if world > 1 else None
+    from face_crop_plus_b200 import distributed as D
     faces_seen = []
 
     def step(images, out):
         res = ctx.pipeline(images, None, target, (256, 256), 0.6, 0.4, "largest", "constant", False, True, cap, out, B, S, S)
         faces_seen.append(res["count"])
-        if world > 1 and out is dev_out:
+        if world > 1:
             # the one collective of the path: landmark / index / matrix metadata of every rank's faces
-            meta[:, :10] = out["landmarks"].view(cap, 10)
-            meta[:, 10] = out["indices"].float() + rank * B
-            meta[:, 11:17] = out["matrices"].view(cap, 6).float()
-            meta[:, 17] = float(res["count"])
-            dist.all_gather_into_tensor(gathered, meta)
+            k = res["count"]
+            rec = D.pack_records(out["landmarks"][:k].cpu().numpy(), out["indices"][:k].cpu().numpy(),
+                                 out["matrices"][:k].cpu().numpy(), out["valid"][:k].cpu().numpy(), rank * B)
+            D.gather_records(rec, cap, device=dev)
         return res
 
     def barrier():

@@ -152,7 +152,7 @@ class Cropper:
         """detect -> un-pad -> align -> parse of cropper.py:815-847 as ONE library call on the uint8 batch."""
         with _lock:
             if self.par_model is not None:
-                self.ctx.set_micro_batch(8, max(int(self.batch_size), 1))
+                self.ctx.set_micro_batch(16, max(int(self.batch_size), 1))
             out = self.ctx.pipeline(np.ascontiguousarray(images), paddings, self.landmarks_target, self.output_size,
                                     self.det_threshold, self.det_model.nms_threshold, self.strategy, self.padding,
                                     self.allow_skew, parse=self.par_model is not None)

@@ -100,19 +100,21 @@ struct fcp_ctx {
     bool own_stream = false;
     std::string error;
     int64_t launches = 0;
-    int det_mb = 8, par_mb = 32;
+    int det_mb = 16, par_mb = 32;
     fcp::Model models[3];
     fcp::Arena arena;          // activations
     fcp::Arena scratch;        // staging of host inputs/outputs, candidate buffers
     std::vector<void*> device_allocs;   // weights etc. freed at destroy
     void* pinned = nullptr; size_t pinned_bytes = 0;
     int sm_count = 148;
-    int use_tc = 0;            // default conv implementation for the model graphs (0 ffma, 1 tcgen05)
+    int use_tc = 1;            // conv implementation of the model graphs: 1 tcgen05 3xTF32 (default), 0 CUDA-core fp32
     // profiling (fcp_profile): event pairs around conv launches + algorithmic work counters
     bool profile = false;
     std::vector<cudaEvent_t> prof_events;   // start0, stop0, start1, stop1, ...
     size_t prof_used = 0;
     double prof_flops = 0, prof_bytes = 0;
+    struct ProfRec { int m, cout, cin, k, stride, tc; };
+    std::vector<ProfRec> prof_recs;     // one per event pair (FCP_TRACE=1 prints a per-shape table)
 };
 
 namespace fcp {

@@ -148,7 +148,9 @@ template <int BN> struct Cfg {
     static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
     static constexpr int STAGES = BN >= 128 ? 3 : (BN == 64 ? 4 : 5);
     static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;           // 64, 128, 256 (powers of two)
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int EPI_LD = 20;                                     // floats per staged row (16 + pad: conflict-free)
+    static constexpr int EPI_BYTES = 8 * 32 * EPI_LD * 4;                 // 8 epilogue warps x 32 pixels x 16 channels
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
 };
 
 template <int BN>
@@ -163,6 +165,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     uint64_t* d_full = bars + 3 * C::STAGES;       // [2]  partial sum of one K-block is complete in TMEM buffer b
     uint64_t* d_empty = d_full + 2;                // [2]  buffer b has been drained to registers
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(d_empty + 2);
+    float* epi_stage = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto stage_a_hi = [&](int s) { return smem + s * C::STAGE_BYTES; };
@@ -300,41 +303,91 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 tc_fence_before();
                 mbar_arrive(&d_empty[buf]);
             }
+            // ---- fused epilogue.  The accumulators are pixel-per-thread (TMEM lane == thread); a 32x16 transpose through
+            // shared memory turns them into channel-contiguous float4s so that residual loads and output stores are
+            // coalesced (4 lanes cover the 64 contiguous bytes of one pixel's 16 channels).
             const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
             const int img = m_tile / tiles_per_img, rem = m_tile - img * tiles_per_img;
-            const int ho = (rem / p.tiles_x) * p.BH + (pix >> p.bw_log2), wo = (rem % p.tiles_x) * BW + (pix & (BW - 1));
-            if (ho >= p.Ho || wo >= p.Wo) continue;
-            const size_t m = ((size_t)img * p.Ho + ho) * p.Wo + wo;
-            size_t res2_pix = m;
-            if (p.res2 && p.res2_h) {
-                int hs = min((int)floorf(ho * ((float)p.res2_h / (float)p.Ho)), p.res2_h - 1);
-                int ws = min((int)floorf(wo * ((float)p.res2_w / (float)p.Wo)), p.res2_w - 1);
-                res2_pix = ((size_t)img * p.res2_h + hs) * p.res2_w + ws;
-            }
-            const int n0 = n_tile * BN + half * HALF;
+            const int ho0 = (rem / p.tiles_x) * p.BH, wo0 = (rem % p.tiles_x) * BW;
+            float* stg = epi_stage + (warp - 6) * 32 * C::EPI_LD;
+            const int sub = lane & 3, rbase = lane >> 2;                      // float4 slot within 16 channels, row within 8
+            size_t m_row[4], r2_row[4];
+            bool ok_row[4];
 #pragma unroll
-            for (int j = 0; j < HALF; ++j) {
-                const int n = n0 + j;
-                if (n < p.Cout) {
-                    float x = acc[j] * __ldg(p.scale + n) + __ldg(p.shift + n);
-                    if (p.res1) x += p.res1[m * p.res1_cs + p.res1_co + n];
-                    x = act_fn(x, p.act, p.slope);
-                    if (p.post_scale != 1.f) x *= p.post_scale;
-                    if (p.res2) x += p.res2[res2_pix * p.res2_cs + p.res2_co + n];
-                    if (p.post_scale2 != 1.f) x *= p.post_scale2;
-                    if (p.res3) x += p.res3[m * p.res3_cs + p.res3_co + n];
-                    acc[j] = x;
+            for (int st = 0; st < 4; ++st) {
+                const int prow = quarter * 32 + rbase + 8 * st;               // pixel of the 128-pixel box
+                const int ho = ho0 + (prow >> p.bw_log2), wo = wo0 + (prow & (BW - 1));
+                ok_row[st] = ho < p.Ho && wo < p.Wo;
+                m_row[st] = ((size_t)img * p.Ho + ho) * p.Wo + wo;
+                r2_row[st] = m_row[st];
+                if (p.res2 && p.res2_h) {
+                    int hs = min((int)floorf(ho * ((float)p.res2_h / (float)p.Ho)), p.res2_h - 1);
+                    int ws = min((int)floorf(wo * ((float)p.res2_w / (float)p.Wo)), p.res2_w - 1);
+                    r2_row[st] = ((size_t)img * p.res2_h + hs) * p.res2_w + ws;
                 }
             }
-            float* dst = p.out + m * p.out_cs + p.out_co + n0;
+            const float* __restrict__ res1 = p.res1;
+            const float* __restrict__ res2 = p.res2;
+            const float* __restrict__ res3 = p.res3;
+            float* __restrict__ outp = p.out;
 #pragma unroll
-            for (int j = 0; j < HALF; j += 4) {
-                if (n0 + j + 3 < p.Cout) {
-                    *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-                } else {
-                    if (n0 + j < p.Cout) dst[j] = acc[j];
-                    if (n0 + j + 1 < p.Cout) dst[j + 1] = acc[j + 1];
-                    if (n0 + j + 2 < p.Cout) dst[j + 2] = acc[j + 2];
+            for (int c16 = 0; c16 < HALF / 16; ++c16) {
+                const int n = n_tile * BN + half * HALF + c16 * 16 + sub * 4;  // first of this lane's 4 channels
+                const bool has_n = n < p.Cout, full4 = n + 3 < p.Cout;
+                // issue every global load of this chunk before touching shared memory: 4 rows x (res1,res2,res3) + scale/shift
+                // (res1 and res2 are never used together by the graphs: one prefetch array serves whichever is set; the rare
+                //  res3 of the RRDB tail is read late)
+                const float* __restrict__ rsrc = res1 ? res1 : res2;
+                const int r_cs = res1 ? p.res1_cs : p.res2_cs, r_co = res1 ? p.res1_co : p.res2_co;
+                float rp[4][4], sc[4], sh[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { sc[e] = n + e < p.Cout ? __ldg(p.scale + n + e) : 0.f; sh[e] = n + e < p.Cout ? __ldg(p.shift + n + e) : 0.f; }
+#pragma unroll
+                for (int st = 0; st < 4; ++st) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) rp[st][e] = 0.f;
+                    if (!ok_row[st] || !has_n || !rsrc) continue;
+                    const size_t rpix = res1 ? m_row[st] : r2_row[st];
+                    if (full4) {
+                        float4 t = __ldg(reinterpret_cast<const float4*>(rsrc + rpix * r_cs + r_co + n));
+                        rp[st][0] = t.x; rp[st][1] = t.y; rp[st][2] = t.z; rp[st][3] = t.w;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (n + e < p.Cout) rp[st][e] = __ldg(rsrc + rpix * r_cs + r_co + n + e);
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(stg + lane * C::EPI_LD + j) =
+                        make_float4(acc[c16 * 16 + j], acc[c16 * 16 + j + 1], acc[c16 * 16 + j + 2], acc[c16 * 16 + j + 3]);
+                __syncwarp();
+                if (!has_n) continue;
+#pragma unroll
+                for (int st = 0; st < 4; ++st) {
+                    if (!ok_row[st]) continue;
+                    float4 a4 = *reinterpret_cast<const float4*>(stg + (rbase + 8 * st) * C::EPI_LD + sub * 4);
+                    float x[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float v = x[e] * sc[e] + sh[e];
+                        if (res1) v += rp[st][e];
+                        v = act_fn(v, p.act, p.slope);
+                        if (p.post_scale != 1.f) v *= p.post_scale;
+                        if (!res1 && res2) v += rp[st][e];
+                        if (p.post_scale2 != 1.f) v *= p.post_scale2;
+                        if (res3 && n + e < p.Cout) v += res3[m_row[st] * p.res3_cs + p.res3_co + n + e];
+                        x[e] = v;
+                    }
+                    float* dst = outp + m_row[st] * p.out_cs + p.out_co + n;
+                    if (full4) {
+                        *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (n + e < p.Cout) dst[e] = x[e];
+                    }
                 }
             }
         }
@@ -391,6 +444,7 @@ bool conv_tc_supported(const ConvOp& op) {
     if (op.stride == 2 && !(wt.k == 1 || wt.k == 3)) return false;
     if ((op.in.cs | op.in.co) & 3) return false;
     if ((size_t)op.out.h * op.out.w < 64) return false;       // pooled 1x1 maps etc. stay on the CUDA-core kernel
+    if (op.res1 && op.res2) return false;                     // the epilogue prefetches one residual source (no graph uses both)
     return encode_fn() != nullptr;
 }
 

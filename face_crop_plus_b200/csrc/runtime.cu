@@ -1,6 +1,7 @@
 // runtime.cu — context, stream-ordered arena, weight ingestion (BN folding + packing) and small host helpers.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 
 #include "common.h"
@@ -231,6 +232,7 @@ int run_conv(fcp_ctx* ctx, const ConvOp& op) {
     const double M = (double)op.out.n * op.out.h * op.out.w, K = (double)w.k * w.k * w.cin;
     ctx->prof_flops += 2.0 * M * w.cout * K;
     ctx->prof_bytes += 4.0 * ((double)op.in.pixels() * w.cin + M * w.cout + K * w.cout);
+    ctx->prof_recs.push_back({(int)M, w.cout, w.cin, w.k, op.stride, tc ? 1 : 0});
     return s;
 }
 
@@ -322,11 +324,27 @@ int fcp_profile_read(fcp_ctx* ctx, double* out4) {
     if (!ctx || !out4) return fail(ctx, FCP_ERR_INVALID, "fcp_profile_read: bad argument");
     FCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     double ms = 0;
+    std::map<std::string, std::pair<double, double>> table;   // shape -> (ms, flops)
+    std::map<std::string, int> counts;
     for (size_t i = 0; i + 1 < ctx->prof_used; i += 2) {
         float t = 0;
         FCP_CUDA(ctx, cudaEventElapsedTime(&t, ctx->prof_events[i], ctx->prof_events[i + 1]));
         ms += t;
+        if (i / 2 < ctx->prof_recs.size()) {
+            const auto& r = ctx->prof_recs[i / 2];
+            char key[128];
+            snprintf(key, sizeof key, "%s k%d s%d cin%-4d cout%-4d M%-8d", r.tc ? "tc  " : "ffma", r.k, r.stride, r.cin, r.cout, r.m);
+            table[key].first += t;
+            table[key].second += 2.0 * r.m * r.cout * (double)r.k * r.k * r.cin;
+            counts[key]++;
+        }
     }
+    if (getenv("FCP_TRACE")) {
+        for (auto& kv : table)
+            fprintf(stderr, "[fcp trace] %s n=%-4d ms=%9.3f  %7.2f TFLOP/s  share=%.3f\n", kv.first.c_str(), counts[kv.first],
+                    kv.second.first, kv.second.second / kv.second.first / 1e9, kv.second.first / ms);
+    }
+    ctx->prof_recs.clear();
     out4[0] = ms; out4[1] = (double)(ctx->prof_used / 2); out4[2] = ctx->prof_flops; out4[3] = ctx->prof_bytes;
     ctx->prof_used = 0; ctx->prof_flops = 0; ctx->prof_bytes = 0;
     return FCP_OK;

@@ -53,9 +53,10 @@ int fcp_set_stream(fcp_ctx* ctx, void* cuda_stream);
 int fcp_sync(fcp_ctx* ctx);
 /* number of kernels this context has launched since creation (bench.py reports it as gpu_launches) */
 int64_t fcp_launch_count(const fcp_ctx* ctx);
-/* images per detector micro-batch / faces per parser micro-batch (bounds the activation arena; default 8 / 32) */
+/* images per detector micro-batch / faces per parser micro-batch (bounds the activation arena; default 16 / 32) */
 int fcp_set_micro_batch(fcp_ctx* ctx, int detect_images, int parse_faces);
-/* convolution kernel used by the model graphs: 0 = CUDA-core fp32, 1 = tcgen05 3xTF32 (same results to fp32 rounding) */
+/* convolution kernel used by the model graphs: 1 = tcgen05 3xTF32 (default), 0 = CUDA-core fp32; both are fp32-accurate.
+ * The environment variable FCP_CONV_IMPL sets the default of new contexts. */
 int fcp_set_conv_impl(fcp_ctx* ctx, int impl);
 
 /* per-kernel timing for bench.py's roofline line: when enabled, every convolution launch is bracketed by CUDA events

@@ -213,7 +213,7 @@ def test_detect_matches_reference_predict(det_ctx, golden, strategy):
     imgs = synth.make_images(n, h, w, seed=int(g["images_seed"]))
     det_ctx.set_micro_batch(2, 32)                     # 3 images -> micro-batches of 2 + 1 (ragged tail)
     out = det_ctx.detect(imgs, 0.6, 0.4, strategy)
-    det_ctx.set_micro_batch(8, 32)
+    det_ctx.set_micro_batch(16, 32)
     assert out["indices"].tolist() == g[f"indices_{strategy}"].tolist()
     assert np.abs(out["landmarks"] - g[f"landmarks_{strategy}"]).max() < TOL
 
@@ -244,9 +244,9 @@ def test_parse_matches_reference(par_ctx, golden, tag):
     crops = synth.make_images(n, h, w, seed=int(g[f"{tag}_seed"]))
     logits = par_ctx.parse_logits(crops)
     assert np.abs(logits - g[f"{tag}_logits64"]).max() < TOL
-    par_ctx.set_micro_batch(8, 2)                      # ragged face micro-batches
+    par_ctx.set_micro_batch(16, 2)                     # ragged face micro-batches
     labels, hist = par_ctx.parse(crops)
-    par_ctx.set_micro_batch(8, 32)
+    par_ctx.set_micro_batch(16, 32)
     diff = labels != g[f"{tag}_labels"]
     if diff.any():   # argmax may flip only where the reference's own top-2 logits are within the float tolerance
         ref_lg = torch.from_numpy(g[f"{tag}_logits64"])
