@@ -88,6 +88,14 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -255,20 +263,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             for (int kb = 0; kb < kblocks; ++kb) {
                 mbar_wait(&full[stage], phase);
-                uint8_t* hi = stage_a_hi(stage);
-                uint8_t* lo = stage_a_lo(stage);
+                const uint32_t hi = smem_u32(stage_a_hi(stage)), lo = smem_u32(stage_a_lo(stage));
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const int off = (row0 + 16 * i) * 128 + chunk * 16;
-                    uint4 v = *reinterpret_cast<uint4*>(hi + off);
+                    const uint32_t off = (row0 + 16 * i) * 128 + chunk * 16;
+                    uint4 v = lds128(hi + off);
                     uint4 h, l;
                     h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
                     l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x)) & 0xFFFFE000u;
                     l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y)) & 0xFFFFE000u;
                     l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z)) & 0xFFFFE000u;
                     l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w)) & 0xFFFFE000u;
-                    *reinterpret_cast<uint4*>(hi + off) = h;
-                    *reinterpret_cast<uint4*>(lo + off) = l;
+                    sts128(hi + off, h);
+                    sts128(lo + off, l);
                 }
                 fence_async_smem();                                           // generic-proxy writes -> visible to the MMA (async proxy)
                 mbar_arrive(&conv[stage]);
@@ -305,88 +312,85 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             }
             // ---- fused epilogue.  The accumulators are pixel-per-thread (TMEM lane == thread); a 32x16 transpose through
             // shared memory turns them into channel-contiguous float4s so that residual loads and output stores are
-            // coalesced (4 lanes cover the 64 contiguous bytes of one pixel's 16 channels).
+            // coalesced (4 lanes cover the 64 contiguous bytes of one pixel's 16 channels).  Kept deliberately compact
+            // (one activation form, no per-element guards on the fast path): an unrolled epilogue overflowed the I-cache.
             const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
             const int img = m_tile / tiles_per_img, rem = m_tile - img * tiles_per_img;
             const int ho0 = (rem / p.tiles_x) * p.BH, wo0 = (rem % p.tiles_x) * BW;
             float* stg = epi_stage + (warp - 6) * 32 * C::EPI_LD;
             const int sub = lane & 3, rbase = lane >> 2;                      // float4 slot within 16 channels, row within 8
-            size_t m_row[4], r2_row[4];
-            bool ok_row[4];
+            const int nb = n_tile * BN + half * HALF + sub * 4;               // this lane's first channel in chunk 0
+            const float* __restrict__ rsrc = p.res1 ? p.res1 : p.res2;        // the graphs never use res1 and res2 together
+            const int r_cs = p.res1 ? p.res1_cs : p.res2_cs, r_co = p.res1 ? p.res1_co : p.res2_co;
+            const bool r_pre = p.res1 != nullptr;
+            const float neg_slope = p.act == FCP_ACT_NONE ? 1.f : (p.act == FCP_ACT_RELU ? 0.f : p.slope);
+            float* optr[4];
+            const float* rptr[4];
+            const float* r3ptr[4];
 #pragma unroll
             for (int st = 0; st < 4; ++st) {
                 const int prow = quarter * 32 + rbase + 8 * st;               // pixel of the 128-pixel box
                 const int ho = ho0 + (prow >> p.bw_log2), wo = wo0 + (prow & (BW - 1));
-                ok_row[st] = ho < p.Ho && wo < p.Wo;
-                m_row[st] = ((size_t)img * p.Ho + ho) * p.Wo + wo;
-                r2_row[st] = m_row[st];
-                if (p.res2 && p.res2_h) {
+                const bool ok = ho < p.Ho && wo < p.Wo;
+                const size_t m = ((size_t)img * p.Ho + ho) * p.Wo + wo;
+                size_t rp = m;
+                if (!r_pre && p.res2_h) {   // nearest resize of the added map (FPN top-down, _layers.py:137-142)
                     int hs = min((int)floorf(ho * ((float)p.res2_h / (float)p.Ho)), p.res2_h - 1);
                     int ws = min((int)floorf(wo * ((float)p.res2_w / (float)p.Wo)), p.res2_w - 1);
-                    r2_row[st] = ((size_t)img * p.res2_h + hs) * p.res2_w + ws;
+                    rp = ((size_t)img * p.res2_h + hs) * p.res2_w + ws;
                 }
+                optr[st] = ok ? p.out + m * p.out_cs + p.out_co + nb : nullptr;
+                rptr[st] = rsrc ? rsrc + rp * r_cs + r_co + nb : nullptr;
+                r3ptr[st] = p.res3 ? p.res3 + m * p.res3_cs + p.res3_co + nb : nullptr;
             }
-            const float* __restrict__ res1 = p.res1;
-            const float* __restrict__ res2 = p.res2;
-            const float* __restrict__ res3 = p.res3;
-            float* __restrict__ outp = p.out;
 #pragma unroll
             for (int c16 = 0; c16 < HALF / 16; ++c16) {
-                const int n = n_tile * BN + half * HALF + c16 * 16 + sub * 4;  // first of this lane's 4 channels
-                const bool has_n = n < p.Cout, full4 = n + 3 < p.Cout;
-                // issue every global load of this chunk before touching shared memory: 4 rows x (res1,res2,res3) + scale/shift
-                // (res1 and res2 are never used together by the graphs: one prefetch array serves whichever is set; the rare
-                //  res3 of the RRDB tail is read late)
-                const float* __restrict__ rsrc = res1 ? res1 : res2;
-                const int r_cs = res1 ? p.res1_cs : p.res2_cs, r_co = res1 ? p.res1_co : p.res2_co;
-                float rp[4][4], sc[4], sh[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) { sc[e] = n + e < p.Cout ? __ldg(p.scale + n + e) : 0.f; sh[e] = n + e < p.Cout ? __ldg(p.shift + n + e) : 0.f; }
-#pragma unroll
-                for (int st = 0; st < 4; ++st) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) rp[st][e] = 0.f;
-                    if (!ok_row[st] || !has_n || !rsrc) continue;
-                    const size_t rpix = res1 ? m_row[st] : r2_row[st];
-                    if (full4) {
-                        float4 t = __ldg(reinterpret_cast<const float4*>(rsrc + rpix * r_cs + r_co + n));
-                        rp[st][0] = t.x; rp[st][1] = t.y; rp[st][2] = t.z; rp[st][3] = t.w;
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (n + e < p.Cout) rp[st][e] = __ldg(rsrc + rpix * r_cs + r_co + n + e);
-                    }
-                }
+                const int n = nb + c16 * 16;
                 __syncwarp();
 #pragma unroll
                 for (int j = 0; j < 16; j += 4)
                     *reinterpret_cast<float4*>(stg + lane * C::EPI_LD + j) =
                         make_float4(acc[c16 * 16 + j], acc[c16 * 16 + j + 1], acc[c16 * 16 + j + 2], acc[c16 * 16 + j + 3]);
                 __syncwarp();
-                if (!has_n) continue;
+                if (n + 3 < p.Cout) {
+                    const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n));
+                    const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n));
+                    float4 rv[4];
 #pragma unroll
-                for (int st = 0; st < 4; ++st) {
-                    if (!ok_row[st]) continue;
-                    float4 a4 = *reinterpret_cast<const float4*>(stg + (rbase + 8 * st) * C::EPI_LD + sub * 4);
-                    float x[4] = {a4.x, a4.y, a4.z, a4.w};
+                    for (int st = 0; st < 4; ++st)
+                        rv[st] = (rptr[st] && optr[st]) ? __ldg(reinterpret_cast<const float4*>(rptr[st] + c16 * 16)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float v = x[e] * sc[e] + sh[e];
-                        if (res1) v += rp[st][e];
-                        v = act_fn(v, p.act, p.slope);
-                        if (p.post_scale != 1.f) v *= p.post_scale;
-                        if (!res1 && res2) v += rp[st][e];
-                        if (p.post_scale2 != 1.f) v *= p.post_scale2;
-                        if (res3 && n + e < p.Cout) v += res3[m_row[st] * p.res3_cs + p.res3_co + n + e];
-                        x[e] = v;
+                    for (int st = 0; st < 4; ++st) {
+                        if (!optr[st]) continue;
+                        float4 x = *reinterpret_cast<const float4*>(stg + (rbase + 8 * st) * C::EPI_LD + sub * 4);
+                        x.x = x.x * sc.x + sh.x; x.y = x.y * sc.y + sh.y; x.z = x.z * sc.z + sh.z; x.w = x.w * sc.w + sh.w;
+                        if (r_pre) { x.x += rv[st].x; x.y += rv[st].y; x.z += rv[st].z; x.w += rv[st].w; }
+                        x.x = x.x > 0.f ? x.x : x.x * neg_slope; x.y = x.y > 0.f ? x.y : x.y * neg_slope;
+                        x.z = x.z > 0.f ? x.z : x.z * neg_slope; x.w = x.w > 0.f ? x.w : x.w * neg_slope;
+                        x.x *= p.post_scale; x.y *= p.post_scale; x.z *= p.post_scale; x.w *= p.post_scale;
+                        if (!r_pre) { x.x += rv[st].x; x.y += rv[st].y; x.z += rv[st].z; x.w += rv[st].w; }
+                        if (r3ptr[st]) {
+                            const float4 r3 = __ldg(reinterpret_cast<const float4*>(r3ptr[st] + c16 * 16));
+                            x.x = x.x * p.post_scale2 + r3.x; x.y = x.y * p.post_scale2 + r3.y;
+                            x.z = x.z * p.post_scale2 + r3.z; x.w = x.w * p.post_scale2 + r3.w;
+                        }
+                        *reinterpret_cast<float4*>(optr[st] + c16 * 16) = x;
                     }
-                    float* dst = outp + m_row[st] * p.out_cs + p.out_co + n;
-                    if (full4) {
-                        *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (n + e < p.Cout) dst[e] = x[e];
+                } else if (n < p.Cout) {
+                    // ragged tail (Cout not a multiple of 4, e.g. the 19-class logits): guarded scalar path
+#pragma unroll 1
+                    for (int st = 0; st < 4; ++st) {
+                        if (!optr[st]) continue;
+#pragma unroll 1
+                        for (int e = 0; e < 4 && n + e < p.Cout; ++e) {
+                            float x = stg[(rbase + 8 * st) * C::EPI_LD + sub * 4 + e] * __ldg(p.scale + n + e) + __ldg(p.shift + n + e);
+                            const float rvs = rptr[st] ? rptr[st][c16 * 16 + e] : 0.f;
+                            if (r_pre) x += rvs;
+                            x = (x > 0.f ? x : x * neg_slope) * p.post_scale;
+                            if (!r_pre) x += rvs;
+                            if (r3ptr[st]) x = x * p.post_scale2 + r3ptr[st][c16 * 16 + e];
+                            optr[st][c16 * 16 + e] = x;
+                        }
                     }
                 }
             }
@@ -444,7 +448,8 @@ bool conv_tc_supported(const ConvOp& op) {
     if (op.stride == 2 && !(wt.k == 1 || wt.k == 3)) return false;
     if ((op.in.cs | op.in.co) & 3) return false;
     if ((size_t)op.out.h * op.out.w < 64) return false;       // pooled 1x1 maps etc. stay on the CUDA-core kernel
-    if (op.res1 && op.res2) return false;                     // the epilogue prefetches one residual source (no graph uses both)
+    if (op.res1 && op.res2) return false;
+    if (op.act == FCP_ACT_SIGMOID) return false;              // one activation form (leaky with slope 0 / 1 / s) in the compact epilogue                     // the epilogue prefetches one residual source (no graph uses both)
     return encode_fn() != nullptr;
 }
 
