@@ -11,9 +11,13 @@
 //
 // Precision (parity bar: landmarks <= 1e-3 px, bit-exact argmax => single-pass TF32/BF16 is not enough):
 //   a = a_hi + a_lo, w = w_hi + w_lo with *_hi = value truncated to TF32;  D += a_hi*w_hi + a_lo*w_hi + a_hi*w_lo.
-//   w_hi/w_lo are split on the host; a_hi/a_lo are split on the fly by 4 converter warps working in shared memory
-//   (elementwise, so the swizzled layout is preserved).  Every operand has its low 13 mantissa bits zeroed, hence the
-//   result does not depend on how the tensor core rounds fp32 -> tf32.
+//   w_hi/w_lo are split on the host and stay in shared memory (B operand, smem descriptors); a_hi/a_lo are split on the
+//   fly by 4 converter warps that read the TMA-landed fp32 tile (one 128-byte pixel row per thread, conflict-free thanks
+//   to the swizzle) and write both parts into TENSOR MEMORY (tcgen05.st), from where the MMA reads its A operand
+//   (tcgen05.mma with A in TMEM).  That halves the shared-memory traffic of the MMAs, removes the converters' smem
+//   stores, and shrinks a pipeline stage to 48 KiB so that 4 stages fit (the K loop is latency-bound, not bandwidth-
+//   bound: measured cycle per stage ~ T_tma + T_convert + T_mma, throughput = stages / cycle).  Every operand has its
+//   low 13 mantissa bits zeroed, hence the result does not depend on how the tensor core rounds fp32 -> tf32.
 //
 //   Measured on B200: the TMEM accumulator add rounds toward zero (~3e-8 relative loss per accumulate, 5e-5 over a
 //   K=4608 chain) - a systematic shrink that a 60-layer network amplifies.  Therefore a TMEM accumulation chain never
@@ -105,6 +109,22 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
                  ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same with the A operand in tensor memory (rows = lanes, one 32-bit column per tf32 element)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 32 columns: thread i of the warp writes its 32 registers to lane (base_lane + i)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+          "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+          "r"(r[30]), "r"(r[31])
+        : "memory");
+}
 // arrives on `bar` when all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -153,9 +173,12 @@ __device__ __forceinline__ float act_fn(float v, int act, float slope) {
 
 template <int BN> struct Cfg {
     static constexpr int B_TILE_BYTES = BN * KB * 4;
-    static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
-    static constexpr int STAGES = BN >= 128 ? 3 : (BN == 64 ? 4 : 5);
-    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;           // 64, 128, 256 (powers of two)
+    static constexpr int STAGE_BYTES = A_TILE_BYTES + 2 * B_TILE_BYTES;   // fp32 A tile + w_hi + w_lo
+    static constexpr int STAGES = BN >= 128 ? 4 : (BN == 64 ? 6 : 7);
+    // tensor memory: [0, 2*BN) two partial-sum buffers; then STAGES x (a_hi 32 cols | a_lo 32 cols)
+    static constexpr int TMEM_A0 = 2 * BN;
+    static constexpr int TMEM_COLS = 512;
+    static_assert(TMEM_A0 + STAGES * 64 <= TMEM_COLS, "tensor memory budget");
     static constexpr int EPI_LD = 20;                                     // floats per staged row (16 + pad: conflict-free)
     static constexpr int EPI_BYTES = 8 * 32 * EPI_LD * 4;                 // 8 epilogue warps x 32 pixels x 16 channels
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
@@ -176,10 +199,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     float* epi_stage = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    auto stage_a_hi = [&](int s) { return smem + s * C::STAGE_BYTES; };
-    auto stage_a_lo = [&](int s) { return smem + s * C::STAGE_BYTES + A_TILE_BYTES; };
-    auto stage_b_hi = [&](int s) { return smem + s * C::STAGE_BYTES + 2 * A_TILE_BYTES; };
-    auto stage_b_lo = [&](int s) { return smem + s * C::STAGE_BYTES + 2 * A_TILE_BYTES + C::B_TILE_BYTES; };
+    auto stage_a = [&](int s) { return smem + s * C::STAGE_BYTES; };
+    auto stage_b_hi = [&](int s) { return smem + s * C::STAGE_BYTES + A_TILE_BYTES; };
+    auto stage_b_lo = [&](int s) { return smem + s * C::STAGE_BYTES + A_TILE_BYTES + C::B_TILE_BYTES; };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&conv[s], 128); mbar_init(&empty[s], 1); }
@@ -217,7 +239,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                         dy = (dy - py) >> 1;
                         dx = (dx - px) >> 1;
                     }
-                    tma_load_4d(stage_a_hi(stage), &p.tmA[map], &full[stage], c0, wo0 + dx, ho0 + dy, img);
+                    tma_load_4d(stage_a(stage), &p.tmA[map], &full[stage], c0, wo0 + dx, ho0 + dy, img);
                     tma_load_2d(stage_b_hi(stage), &p.tmBhi, &full[stage], tap * p.Cin + c0, n_tile * BN);
                     tma_load_2d(stage_b_lo(stage), &p.tmBlo, &full[stage], tap * p.Cin + c0, n_tile * BN);
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -238,17 +260,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     mbar_wait(&conv[stage], phase);                           // operands (hi/lo) ready in smem
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + buf * BN;
-                    const uint64_t a_hi = umma_desc(smem_u32(stage_a_hi(stage))), a_lo = umma_desc(smem_u32(stage_a_lo(stage)));
+                    const uint32_t a_hi = tmem_base + C::TMEM_A0 + stage * 64, a_lo = a_hi + 32;   // A operand: tensor memory
                     const uint64_t b_hi = umma_desc(smem_u32(stage_b_hi(stage))), b_lo = umma_desc(smem_u32(stage_b_lo(stage)));
-                    // 8 tf32 = 32 bytes along K inside the 128-byte swizzle span -> +2 in the (addr >> 4) field per K-step.
+                    // one K-step = 8 tf32: +8 TMEM columns for A, +32 bytes (+2 in the addr>>4 field) inside B's swizzle span.
                     // Small terms first: while the accumulator is tiny its round-toward-zero losses are negligible.
 #pragma unroll
                     for (int k = 0; k < KB / 8; ++k) {
-                        umma_tf32(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, k != 0);
-                        umma_tf32(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
+                        umma_tf32_ts(d_tmem, a_lo + 8 * k, b_hi + 2 * k, idesc, k != 0);
+                        umma_tf32_ts(d_tmem, a_hi + 8 * k, b_lo + 2 * k, idesc, 1);
                     }
 #pragma unroll
-                    for (int k = 0; k < KB / 8; ++k) umma_tf32(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, 1);
+                    for (int k = 0; k < KB / 8; ++k) umma_tf32_ts(d_tmem, a_hi + 8 * k, b_hi + 2 * k, idesc, 1);
                     umma_commit(&empty[stage]);                               // smem slot reusable once these MMAs retire
                     umma_commit(&d_full[buf]);                                // partial sum of this K-block complete
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -257,27 +279,33 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         }
     } else if (warp < 6) {
         // ================================================================= hi/lo converters (warps 2..5, 128 threads)
-        const int t = threadIdx.x - 64;
-        const int chunk = t & 7, row0 = t >> 3;                               // 16-byte chunk of row (row0 + 16*i)
+        // thread <-> one pixel row of the tile == one TMEM lane (a warp may only touch lanes 32*(warp%4)..+31)
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
         int stage = 0; uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             for (int kb = 0; kb < kblocks; ++kb) {
                 mbar_wait(&full[stage], phase);
-                const uint32_t hi = smem_u32(stage_a_hi(stage)), lo = smem_u32(stage_a_lo(stage));
+                const uint32_t src = smem_u32(stage_a(stage)) + row * 128;
+                uint4 v[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const uint32_t off = (row0 + 16 * i) * 128 + chunk * 16;
-                    uint4 v = lds128(hi + off);
-                    uint4 h, l;
-                    h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
-                    l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x)) & 0xFFFFE000u;
-                    l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y)) & 0xFFFFE000u;
-                    l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z)) & 0xFFFFE000u;
-                    l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w)) & 0xFFFFE000u;
-                    sts128(hi + off, h);
-                    sts128(lo + off, l);
+                for (int c = 0; c < 8; ++c) v[c] = lds128(src + (uint32_t)((c ^ (row & 7)) << 4));   // undo the 128B swizzle: logical chunk c
+                uint32_t hi[32], lo[32];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t w[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        hi[4 * c + e] = w[e] & 0xFFFFE000u;
+                        lo[4 * c + e] = __float_as_uint(__uint_as_float(w[e]) - __uint_as_float(hi[4 * c + e])) & 0xFFFFE000u;
+                    }
                 }
-                fence_async_smem();                                           // generic-proxy writes -> visible to the MMA (async proxy)
+                const uint32_t dst = tmem_base + C::TMEM_A0 + stage * 64 + lane_addr;
+                tmem_st32(dst, hi);
+                tmem_st32(dst + 32, lo);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
                 mbar_arrive(&conv[stage]);
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
