@@ -24,14 +24,17 @@
 //   spans more than ONE K-block: the 8 small-term MMAs (a_lo*w_hi, a_hi*w_lo) go first, the 4 a_hi*w_hi MMAs last, then
 //   the block's partial sum is drained to fp32 registers and added there with round-to-nearest.
 //
-// CTA = 14 warps, persistent over output tiles (128 pixels x BN channels):
+// CTA = 15 warps, persistent over output tiles (128 pixels x BN channels):
 //   warp 0      TMA producer          full[s]  <- TMA bytes          (waits empty[s])
-//   warps 2-5   hi/lo converters      conv[s]  <- 128 arrivals       (wait full[s])
-//   warp 1      MMA issuer (1 lane)   empty[s], d_full[b] <- tcgen05.commit     (waits conv[s], d_empty[b])
-//   warps 6-13  accumulate+epilogue   d_empty[b] <- 256 arrivals     (wait d_full[b]); per K-block TMEM -> regs (+=),
+//   warps 2-5   hi/lo converters      conv[s]  <- 4 arrivals (1/warp) (wait full[s])
+//   warps 1,14  MMA issuers (1 lane each, alternating K-blocks)  empty[s], d_full[b] <- tcgen05.commit (wait conv[s], d_empty[b])
+//   warps 6-13  accumulate+epilogue   d_empty[b] <- 8 arrivals (1/warp) (wait d_full[b]); per K-block TMEM -> regs (+=),
 //               after the last K-block: fused epilogue -> HBM.  Warp w owns TMEM lanes 32*(w%4).. and half of the columns.
 // Two TMEM partial-sum buffers let the drain of K-block i overlap the MMAs of K-block i+1.
 #include <cuda.h>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
 
 #include "common.h"
 
@@ -42,7 +45,7 @@ namespace {
 constexpr int TILE_M = 128;
 constexpr int KB = 32;                         // channels per K-block (128 bytes of fp32)
 constexpr int A_TILE_BYTES = TILE_M * KB * 4;  // 16 KiB
-constexpr int NUM_THREADS = 448;
+constexpr int NUM_THREADS = 480;
 
 struct alignas(64) TcParams {
     CUtensorMap tmA[4];                        // input, one per (row parity, column parity); stride 1 uses [0]
@@ -55,6 +58,7 @@ struct alignas(64) TcParams {
     int act; float slope;
     float post_scale; const float* res2; int res2_cs, res2_co, res2_h, res2_w;
     float post_scale2; const float* res3; int res3_cs, res3_co;
+    long long* dbg;                            // FCP_EXP_TIMELINE: clock64 stamps of CTA 0, [g][16]
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -69,12 +73,15 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+template <bool BACKOFF = false>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done;
     const uint32_t addr = smem_u32(bar);
     do {
         asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
                      : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        // non-critical roles back off: 13 warps spinning on try_wait starve the MMA-issuing threads of issue slots
+        if (BACKOFF && !done) __nanosleep(32);
     } while (!done);
 }
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
@@ -100,6 +107,11 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+#ifdef FCP_EXP_TIMELINE
+#define TL(g, ev) do { if (p.dbg && blockIdx.x == 0 && (g) < 512) p.dbg[(g) * 16 + (ev)] = clock64(); } while (0)
+#else
+#define TL(g, ev) do { } while (0)
+#endif
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -204,8 +216,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     auto stage_b_lo = [&](int s) { return smem + s * C::STAGE_BYTES + A_TILE_BYTES + C::B_TILE_BYTES; };
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&conv[s], 128); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&d_full[a], 1); mbar_init(&d_empty[a], 256); }
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&conv[s], 4); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&d_full[a], 1); mbar_init(&d_empty[a], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_base_smem, C::TMEM_COLS);
@@ -222,7 +234,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     if (warp == 0) {
         // ================================================================================== TMA producer
         if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
+            int stage = 0; uint32_t phase = 0; uint32_t gp = 0; (void)gp;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
                 const int img = m_tile / tiles_per_img, rem = m_tile - img * tiles_per_img;
@@ -230,7 +242,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 for (int kb = 0; kb < kblocks; ++kb) {
                     const int tap = kb / cchunks, c0 = (kb - tap * cchunks) * KB;
                     const int r = tap / p.KW, s = tap - r * p.KW;
-                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_wait<true>(&empty[stage], phase ^ 1);
+                    TL(gp, 0);
                     mbar_expect_tx(&full[stage], A_TILE_BYTES + 2 * C::B_TILE_BYTES);
                     int dy = r - p.pad, dx = s - p.pad, map = 0;
                     if (p.stride == 2) {   // input row 2*ho + dy lives in parity view (dy & 1) at row ho + (dy - (dy & 1)) / 2
@@ -242,37 +255,47 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     tma_load_4d(stage_a(stage), &p.tmA[map], &full[stage], c0, wo0 + dx, ho0 + dy, img);
                     tma_load_2d(stage_b_hi(stage), &p.tmBhi, &full[stage], tap * p.Cin + c0, n_tile * BN);
                     tma_load_2d(stage_b_lo(stage), &p.tmBlo, &full[stage], tap * p.Cin + c0, n_tile * BN);
+                    TL(gp, 1); ++gp;
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
-    } else if (warp == 1) {
-        // ==================================================================================== MMA issuer
+    } else if (warp == 1 || warp == 14) {
+        // ============================================================== MMA issuers (warp 1: even K-blocks, warp 14: odd)
         if (lane == 0) {
             // instruction descriptor: D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10), both K-major, N>>3 at bit 17, M>>4 at bit 24
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+            // Issuing a tcgen05.mma blocks the thread for about its execution time, and every barrier wait costs a few
+            // hundred cycles; with a single issuer the tensor pipe idled ~40% of each K-block.  Two issuers alternate
+            // K-blocks (issuer i owns partial-sum buffer i), so one thread's waits overlap the other's MMAs.
+            const uint32_t me = warp == 1 ? 0u : 1u;
+            uint32_t g = 0;                                                   // K-blocks so far (all tiles)
             int stage = 0; uint32_t phase = 0;
-            uint32_t g = 0;                                                   // K-blocks issued so far (all tiles)
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 for (int kb = 0; kb < kblocks; ++kb, ++g) {
-                    const uint32_t buf = g & 1;
-                    mbar_wait(&d_empty[buf], ((g >> 1) & 1) ^ 1);             // partial-sum buffer drained
-                    mbar_wait(&conv[stage], phase);                           // operands (hi/lo) ready in smem
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + buf * BN;
-                    const uint32_t a_hi = tmem_base + C::TMEM_A0 + stage * 64, a_lo = a_hi + 32;   // A operand: tensor memory
-                    const uint64_t b_hi = umma_desc(smem_u32(stage_b_hi(stage))), b_lo = umma_desc(smem_u32(stage_b_lo(stage)));
-                    // one K-step = 8 tf32: +8 TMEM columns for A, +32 bytes (+2 in the addr>>4 field) inside B's swizzle span.
-                    // Small terms first: while the accumulator is tiny its round-toward-zero losses are negligible.
+                    if ((g & 1) == me) {
+                        const uint32_t buf = me;
+                        mbar_wait(&d_empty[buf], ((g >> 1) & 1) ^ 1);         // partial-sum buffer drained
+                        TL(g, 2);
+                        mbar_wait(&conv[stage], phase);                       // operands (hi/lo) ready
+                        TL(g, 3);
+                        tc_fence_after();
+                        const uint32_t d_tmem = tmem_base + buf * BN;
+                        const uint32_t a_hi = tmem_base + C::TMEM_A0 + stage * 64, a_lo = a_hi + 32;   // A operand: tensor memory
+                        const uint64_t b_hi = umma_desc(smem_u32(stage_b_hi(stage))), b_lo = umma_desc(smem_u32(stage_b_lo(stage)));
+                        // one K-step = 8 tf32: +8 TMEM columns for A, +32 bytes (+2 in the addr>>4 field) inside B's swizzle span.
+                        // Small terms first: while the accumulator is tiny its round-toward-zero losses are negligible.
 #pragma unroll
-                    for (int k = 0; k < KB / 8; ++k) {
-                        umma_tf32_ts(d_tmem, a_lo + 8 * k, b_hi + 2 * k, idesc, k != 0);
-                        umma_tf32_ts(d_tmem, a_hi + 8 * k, b_lo + 2 * k, idesc, 1);
+                        for (int k = 0; k < KB / 8; ++k) {
+                            umma_tf32_ts(d_tmem, a_lo + 8 * k, b_hi + 2 * k, idesc, k != 0);
+                            umma_tf32_ts(d_tmem, a_hi + 8 * k, b_lo + 2 * k, idesc, 1);
+                        }
+#pragma unroll
+                        for (int k = 0; k < KB / 8; ++k) umma_tf32_ts(d_tmem, a_hi + 8 * k, b_hi + 2 * k, idesc, 1);
+                        umma_commit(&empty[stage]);                           // smem slot + TMEM A slot reusable once these MMAs retire
+                        umma_commit(&d_full[buf]);                            // partial sum of this K-block complete
+                        TL(g, 4);
                     }
-#pragma unroll
-                    for (int k = 0; k < KB / 8; ++k) umma_tf32_ts(d_tmem, a_hi + 8 * k, b_hi + 2 * k, idesc, 1);
-                    umma_commit(&empty[stage]);                               // smem slot reusable once these MMAs retire
-                    umma_commit(&d_full[buf]);                                // partial sum of this K-block complete
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -283,10 +306,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-        int stage = 0; uint32_t phase = 0;
+        int stage = 0; uint32_t phase = 0; uint32_t gc = 0; (void)gc;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             for (int kb = 0; kb < kblocks; ++kb) {
-                mbar_wait(&full[stage], phase);
+                mbar_wait<true>(&full[stage], phase);
+                if (warp == 2 && lane == 0) TL(gc, 5);
                 const uint32_t src = smem_u32(stage_a(stage)) + row * 128;
                 uint4 v[8];
 #pragma unroll
@@ -306,11 +330,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 tmem_st32(dst + 32, lo);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
-                mbar_arrive(&conv[stage]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&conv[stage]);                     // one arrival per warp
+                if (warp == 2 && lane == 0) TL(gc, 6);
+                ++gc;
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else {
+    } else if (warp < 14) {
         // ============================================================ accumulate + epilogue (warps 6..13, 256 threads)
         constexpr int HALF = BN / 2;                                          // columns owned by this warp
         constexpr int CH = HALF >= 32 ? 32 : 16;                              // columns per tcgen05.ld
@@ -326,7 +353,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             for (int j = 0; j < HALF; ++j) acc[j] = 0.f;
             for (int kb = 0; kb < kblocks; ++kb, ++g) {
                 const uint32_t buf = g & 1;
-                mbar_wait(&d_full[buf], (g >> 1) & 1);
+                mbar_wait<true>(&d_full[buf], (g >> 1) & 1);
+                if (warp == 6 && lane == 0) TL(g, 7);
                 tc_fence_after();
 #pragma unroll
                 for (int cb = 0; cb < NCH; ++cb) {
@@ -336,7 +364,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     for (int j = 0; j < CH; ++j) acc[cb * CH + j] += v[j];     // round-to-nearest fp32 running sum
                 }
                 tc_fence_before();
-                mbar_arrive(&d_empty[buf]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&d_empty[buf]);
+                if (warp == 6 && lane == 0) TL(g, 8);
             }
             // ---- fused epilogue.  The accumulators are pixel-per-thread (TMEM lane == thread); a 32x16 transpose through
             // shared memory turns them into channel-contiguous float4s so that residual loads and output stores are
@@ -532,6 +562,27 @@ int launch_conv_tc(fcp_ctx* ctx, const ConvOp& op) {
     p.act = op.act; p.slope = op.slope;
     p.post_scale = op.post_scale; p.res2 = op.res2; p.res2_cs = op.res2_cs; p.res2_co = op.res2_co; p.res2_h = op.res2_h; p.res2_w = op.res2_w;
     p.post_scale2 = op.post_scale2; p.res3 = op.res3; p.res3_cs = op.res3_cs; p.res3_co = op.res3_co;
+#ifdef FCP_EXP_TIMELINE
+    static int shots = 0;
+    const bool shoot = getenv("FCP_TC_TIMELINE") && wt.k == 3 && wt.cin == 256 && wt.cout == 256 && shots < 1 && p.N * p.Ho * p.Wo >= 65536;
+    long long* dbg = nullptr;
+    if (shoot) { cudaMalloc(&dbg, 512 * 16 * 8); cudaMemset(dbg, 0, 512 * 16 * 8); p.dbg = dbg; ++shots; }
+    int rc = BN == 128 ? launch<128>(ctx, p) : (BN == 64 ? launch<64>(ctx, p) : launch<32>(ctx, p));
+    if (shoot) {
+        cudaStreamSynchronize(ctx->stream);
+        std::vector<long long> h(512 * 16);
+        cudaMemcpy(h.data(), dbg, 512 * 16 * 8, cudaMemcpyDeviceToHost);
+        long long t0 = h[100 * 16 + 0];
+        fprintf(stderr, "[timeline] g: prod_wait_empty prod_issued | mma_dempty mma_conv mma_issued | conv_full conv_done | drain_dfull drain_done\n");
+        for (int g = 100; g < 124; ++g) {
+            fprintf(stderr, "[timeline] %3d:", g);
+            for (int e = 0; e < 9; ++e) fprintf(stderr, " %7lld", h[g * 16 + e] ? h[g * 16 + e] - t0 : -1);
+            fprintf(stderr, "\n");
+        }
+        cudaFree(dbg);
+    }
+    return rc;
+#endif
     if (BN == 128) return launch<128>(ctx, p);
     if (BN == 64) return launch<64>(ctx, p);
     return launch<32>(ctx, p);
