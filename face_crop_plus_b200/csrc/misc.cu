@@ -15,17 +15,20 @@ __device__ __forceinline__ float act_fn(float v, int act, float slope) {
 
 // ------------------------------------------------------------------------------------------------ stem 7x7/s2
 // body.conv1+bn1+relu (torchvision resnet.py:268-270) and cp.resnet.conv1+bn1+relu (_layers.py:262-263).
-// CTA = 8x32 output pixels x 64 channels; input patch 21x69x3 and the 147x64 filter bank live in shared memory.
-constexpr int ST_TH = 8, ST_TW = 32, ST_PH = (ST_TH - 1) * 2 + 7, ST_PW = (ST_TW - 1) * 2 + 7;
+// CTA = 4x128 output pixels x 64 channels, 256 threads; thread = 4 pixels (same row, 32 apart) x 32 channels, i.e. 128
+// fp32 accumulators.  The input patch (13 x 261 x 3) lives in shared memory as three channel planes so that a warp's
+// float2 loads (columns 2x, 2x+1 of consecutive pixels) are conflict-free; the 147x64 filter bank is read with
+// warp-broadcast float4 loads.  Per (row tap, channel): 16 LDS.64 + 56 LDS.128 feed 896 FFMAs -> FMA-pipe bound.
+constexpr int ST_TH = 4, ST_TW = 128, ST_PH = (ST_TH - 1) * 2 + 7, ST_PW = (ST_TW - 1) * 2 + 7, ST_LD = ST_PW + 1;
 
 template <int MODE>
-__global__ void __launch_bounds__(256) stem7_kernel(const void* __restrict__ src, int N, int H, int W,
-                                                    const float* __restrict__ wkn, const float* __restrict__ scale,
-                                                    const float* __restrict__ shift, float* __restrict__ out, int Ho,
-                                                    int Wo, int out_cs, int out_co) {
+__global__ void __launch_bounds__(256, 1) stem7_kernel(const void* __restrict__ src, int N, int H, int W,
+                                                       const float* __restrict__ wkn, const float* __restrict__ scale,
+                                                       const float* __restrict__ shift, float* __restrict__ out, int Ho,
+                                                       int Wo, int out_cs, int out_co) {
     extern __shared__ __align__(16) float sm[];
     float* sw = sm;                       // [147][64]
-    float* sp = sm + 147 * 64;            // [ST_PH][ST_PW][3]
+    float* sp = sm + 147 * 64;            // [3][ST_PH][ST_LD]
     const int tid = threadIdx.x;
     const int n = blockIdx.z;
     const int ho0 = blockIdx.y * ST_TH, wo0 = blockIdx.x * ST_TW;
@@ -49,41 +52,63 @@ __global__ void __launch_bounds__(256) stem7_kernel(const void* __restrict__ src
                 v = static_cast<const float*>(src)[pix * 3 + c];
             }
         }
-        sp[i] = v;
+        sp[(c * ST_PH + py) * ST_LD + px] = v;
     }
     __syncthreads();
-    const int tx = tid % ST_TW, ty = tid / ST_TW;
-    float acc[64];
+    const int half = tid >> 7;            // output channels [32*half, 32*half+32)
+    const int g = tid & 127;
+    const int xi = g & 31, ty = g >> 5;   // pixels (ty, xi + 32*i), i = 0..3
+    float acc[4][32];
 #pragma unroll
-    for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[i][j] = 0.f;
     for (int r = 0; r < 7; ++r) {
-        for (int s = 0; s < 7; ++s) {
-            const float* pin = sp + ((ty * 2 + r) * ST_PW + tx * 2 + s) * 3;
-            const float* pw = sw + (r * 7 + s) * 3 * 64;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                float x = pin[c];
+        for (int c = 0; c < 3; ++c) {
+            const float* prow = sp + (c * ST_PH + ty * 2 + r) * ST_LD;
+            float x[4][8];
 #pragma unroll
-                for (int j = 0; j < 64; j += 4) {
-                    float4 w4 = *reinterpret_cast<const float4*>(pw + c * 64 + j);
-                    acc[j] = fmaf(x, w4.x, acc[j]);
-                    acc[j + 1] = fmaf(x, w4.y, acc[j + 1]);
-                    acc[j + 2] = fmaf(x, w4.z, acc[j + 2]);
-                    acc[j + 3] = fmaf(x, w4.w, acc[j + 3]);
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float2 v = *reinterpret_cast<const float2*>(prow + 2 * (xi + 32 * i) + 2 * q);
+                    x[i][2 * q] = v.x;
+                    x[i][2 * q + 1] = v.y;
+                }
+#pragma unroll
+            for (int s = 0; s < 7; ++s) {
+                const float* pw = sw + ((r * 7 + s) * 3 + c) * 64 + half * 32;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(pw + j);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        acc[i][j] = fmaf(x[i][s], w4.x, acc[i][j]);
+                        acc[i][j + 1] = fmaf(x[i][s], w4.y, acc[i][j + 1]);
+                        acc[i][j + 2] = fmaf(x[i][s], w4.z, acc[i][j + 2]);
+                        acc[i][j + 3] = fmaf(x[i][s], w4.w, acc[i][j + 3]);
+                    }
                 }
             }
         }
     }
-    int ho = ho0 + ty, wo = wo0 + tx;
-    if (ho < Ho && wo < Wo) {
-        float* dst = out + (((size_t)n * Ho + ho) * Wo + wo) * out_cs + out_co;
+    const int ho = ho0 + ty;
+    if (ho >= Ho) return;
 #pragma unroll
-        for (int j = 0; j < 64; j += 4) {
+    for (int i = 0; i < 4; ++i) {
+        const int wo = wo0 + xi + 32 * i;
+        if (wo >= Wo) continue;
+        float* dst = out + (((size_t)n * Ho + ho) * Wo + wo) * out_cs + out_co + half * 32;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 sc = *reinterpret_cast<const float4*>(scale + half * 32 + j);
+            const float4 sh = *reinterpret_cast<const float4*>(shift + half * 32 + j);
             float4 o;
-            o.x = fmaxf(acc[j] * scale[j] + shift[j], 0.f);
-            o.y = fmaxf(acc[j + 1] * scale[j + 1] + shift[j + 1], 0.f);
-            o.z = fmaxf(acc[j + 2] * scale[j + 2] + shift[j + 2], 0.f);
-            o.w = fmaxf(acc[j + 3] * scale[j + 3] + shift[j + 3], 0.f);
+            o.x = fmaxf(acc[i][j] * sc.x + sh.x, 0.f);
+            o.y = fmaxf(acc[i][j + 1] * sc.y + sh.y, 0.f);
+            o.z = fmaxf(acc[i][j + 2] * sc.z + sh.z, 0.f);
+            o.w = fmaxf(acc[i][j + 3] * sc.w + sh.w, 0.f);
             *reinterpret_cast<float4*>(dst + j) = o;
         }
     }
@@ -223,7 +248,7 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, int HW, int C,
 
 int launch_stem7(fcp_ctx* ctx, const void* src, int mode, int n, int h, int w, const float* w_kn, const float* scale,
                  const float* shift, Tensor out) {
-    size_t smem = (147 * 64 + ST_PH * ST_PW * 3) * sizeof(float);
+    size_t smem = (147 * 64 + 3 * ST_PH * ST_LD) * sizeof(float);
     static bool configured = false;
     if (!configured) {
         FCP_CUDA(ctx, cudaFuncSetAttribute(stem7_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
