@@ -191,6 +191,7 @@ int launch_parse_prep(fcp_ctx* ctx, const uint8_t* crops, int f, int h, int w, f
 int launch_parse_tail(fcp_ctx* ctx, const float* logits, int layout_nhwc, int cs, int f, int fh, int fw, int h, int w,
                       uint8_t* labels, int32_t* hist);
 int launch_masks(fcp_ctx* ctx, const uint8_t* labels, size_t count, const uint8_t* lut_dev, uint8_t* out);
+int launch_upsample2x(fcp_ctx* ctx, Tensor in, Tensor out);   // out = nearest x2 upsample of in
 int launch_nhwc_to_nchw(fcp_ctx* ctx, const float* in, int n, int h, int w, int c, int cs, float* out);
 
 // enhance tail: conv_last output [n,4h,4w,3(+pad)] -> bicubic x0.25 -> clamp*255 round, written NCHW f32 [3,h,w]

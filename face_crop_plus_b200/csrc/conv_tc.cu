@@ -45,7 +45,11 @@ namespace {
 constexpr int TILE_M = 128;
 constexpr int KB = 32;                         // channels per K-block (128 bytes of fp32)
 constexpr int A_TILE_BYTES = TILE_M * KB * 4;  // 16 KiB
-constexpr int NUM_THREADS = 480;
+// MMA-issuing warps (warp 1 and warp 14).  Must stay 2: each partial-sum buffer (g & 1) then has exactly one issuer, so a
+// parity wait on d_empty can never be more than one phase ahead (with 3 issuers the same buffer is touched out of
+// order and mbarrier parity waits alias -> corrupted sums and a deadlock; measured the hard way).
+constexpr int NUM_ISSUERS = 2;
+constexpr int NUM_THREADS = 32 * (14 + NUM_ISSUERS - 1);
 
 struct alignas(64) TcParams {
     CUtensorMap tmA[4];                        // input, one per (row parity, column parity); stride 1 uses [0]
@@ -260,21 +264,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 }
             }
         }
-    } else if (warp == 1 || warp == 14) {
+    } else if (warp == 1 || warp >= 14) {
         // ============================================================== MMA issuers (warp 1: even K-blocks, warp 14: odd)
         if (lane == 0) {
             // instruction descriptor: D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10), both K-major, N>>3 at bit 17, M>>4 at bit 24
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
             // Issuing a tcgen05.mma blocks the thread for about its execution time, and every barrier wait costs a few
-            // hundred cycles; with a single issuer the tensor pipe idled ~40% of each K-block.  Two issuers alternate
-            // K-blocks (issuer i owns partial-sum buffer i), so one thread's waits overlap the other's MMAs.
-            const uint32_t me = warp == 1 ? 0u : 1u;
+            // hundred cycles; with a single issuer the tensor pipe idled ~40% of each K-block.  NUM_ISSUERS threads take
+            // K-blocks round-robin, so one thread's waits overlap the others' MMAs.
+            const uint32_t me = warp == 1 ? 0u : (uint32_t)(warp - 13);
             uint32_t g = 0;                                                   // K-blocks so far (all tiles)
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 for (int kb = 0; kb < kblocks; ++kb, ++g) {
-                    if ((g & 1) == me) {
-                        const uint32_t buf = me;
+                    if (g % NUM_ISSUERS == me) {
+                        const uint32_t buf = g & 1;
                         mbar_wait(&d_empty[buf], ((g >> 1) & 1) ^ 1);         // partial-sum buffer drained
                         TL(g, 2);
                         mbar_wait(&conv[stage], phase);                       // operands (hi/lo) ready

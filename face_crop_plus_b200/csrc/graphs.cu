@@ -50,6 +50,19 @@ bool Exec::conv(const std::string& name, Tensor in, Tensor out, int stride, int 
     ConvOp op = extra;
     op.in = in; op.out = out; op.wt = wt; op.stride = stride; op.pad = pad; op.act = act;
     op.impl = ctx->use_tc;
+    if (op.up_in && op.impl == 1 && in.c % 32 == 0) {
+        // the tensor-core kernel needs a dense input for its TMA boxes: materialise the nearest x2 upsample (HBM-bound copy)
+        Tensor up = alloc(in.n, in.h * 2, in.w * 2, in.c);
+        if (!ok()) return false;
+        op.in = up;
+        op.up_in = 0;
+        if (!dry) {
+            status = launch_upsample2x(ctx, in, up);
+            if (ok()) status = run_conv(ctx, op);
+        }
+        free(up);
+        return ok();
+    }
     if (dry) return true;
     status = run_conv(ctx, op);
     return ok();

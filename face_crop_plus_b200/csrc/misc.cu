@@ -232,6 +232,24 @@ __global__ void channel_affine_kernel(const float* __restrict__ in, int in_cs, i
     *reinterpret_cast<float4*>(out + p * out_cs + out_co + c) = o;
 }
 
+// ------------------------------------------------------------------------ nearest x2 upsample (F.interpolate, scale 2)
+// Materialises the upsampled map so the following 3x3 conv can run on the tensor-core kernel (TMA boxes need a dense
+// input): _layers.py:334-344 (BiSeNet context path), rrdb.py:78-79 (RRDBNet upconv1/2).  HBM-bound float4 copy.
+__global__ void upsample2x_kernel(const float* __restrict__ in, int H, int W, int C, int in_cs, int in_co,
+                                  float* __restrict__ out, int out_cs, int out_co, size_t total) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c4n = C / 4;
+    const int c = (idx % c4n) * 4;
+    size_t p = idx / c4n;
+    const int wo = p % (2 * W);
+    size_t t = p / (2 * W);
+    const int ho = t % (2 * H);
+    const size_t n = t / (2 * H);
+    const float4 v = *reinterpret_cast<const float4*>(in + ((n * H + (ho >> 1)) * W + (wo >> 1)) * in_cs + in_co + c);
+    *reinterpret_cast<float4*>(out + p * out_cs + out_co + c) = v;
+}
+
 // ----------------------------------------------------------------------------------------- layout conversions
 __global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, int HW, int C, int cs, int co,
                                     float* __restrict__ out, size_t total) {
@@ -301,6 +319,14 @@ int launch_channel_affine(fcp_ctx* ctx, Tensor in, const float* mul_nc, const fl
     size_t total = in.pixels() * (in.c / 4);
     channel_affine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(
         in.p, in.cs, in.co, (size_t)in.h * in.w, in.c, mul_nc, addvec_nc, add_self, out.p, out.cs, out.co, total);
+    FCP_KERNEL_CHECK(ctx);
+    return FCP_OK;
+}
+
+int launch_upsample2x(fcp_ctx* ctx, Tensor in, Tensor out) {
+    size_t total = out.pixels() * (in.c / 4);
+    upsample2x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(in.p, in.h, in.w, in.c, in.cs, in.co, out.p,
+                                                                               out.cs, out.co, total);
     FCP_KERNEL_CHECK(ctx);
     return FCP_OK;
 }
