@@ -187,22 +187,28 @@ __device__ __forceinline__ float act_fn(float v, int act, float slope) {
     return v;
 }
 
-template <int BN> struct Cfg {
+// RES: the tile's residual operand (bottleneck shortcut / FPN / RRDB skip) is prefetched with cp.async into shared
+// memory while the K loop runs, so the epilogue never waits on HBM; it costs pipeline stages (shared-memory budget).
+template <int BN, bool RES> struct Cfg {
     static constexpr int B_TILE_BYTES = BN * KB * 4;
     static constexpr int STAGE_BYTES = A_TILE_BYTES + 2 * B_TILE_BYTES;   // fp32 A tile + w_hi + w_lo
-    static constexpr int STAGES = BN >= 128 ? 4 : (BN == 64 ? 6 : 7);
+    static constexpr int STAGES = RES ? (BN >= 128 ? 2 : (BN == 64 ? 4 : 6)) : (BN >= 128 ? 3 : (BN == 64 ? 5 : 7));
     // tensor memory: [0, 2*BN) two partial-sum buffers; then STAGES x (a_hi 32 cols | a_lo 32 cols)
     static constexpr int TMEM_A0 = 2 * BN;
     static constexpr int TMEM_COLS = 512;
     static_assert(TMEM_A0 + STAGES * 64 <= TMEM_COLS, "tensor memory budget");
-    static constexpr int EPI_LD = 20;                                     // floats per staged row (16 + pad: conflict-free)
-    static constexpr int EPI_BYTES = 8 * 32 * EPI_LD * 4;                 // 8 epilogue warps x 32 pixels x 16 channels
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
+    static constexpr int EPI_CW = BN >= 64 ? 32 : 16;                     // channels per epilogue chunk (32 -> full 128-byte lines)
+    static constexpr int EPI_LD = EPI_CW + 4;                             // floats per staged row (+4 pad: conflict-free float4s)
+    static constexpr int EPI_BYTES = 8 * 32 * EPI_LD * 4;                 // 8 epilogue warps x 32 pixels x EPI_CW channels
+    static constexpr int RES_LD = BN / 2 + 4;                             // residual rows: BN/2 channels + pad
+    static constexpr int RES_BYTES = RES ? 8 * 32 * RES_LD * 4 : 0;       // 8 epilogue warps x 32 pixels x BN/2 channels
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES + RES_BYTES;
+    static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
-template <int BN>
+template <int BN, bool RES>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, RES>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -213,6 +219,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     uint64_t* d_empty = d_full + 2;                // [2]  buffer b has been drained to registers
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(d_empty + 2);
     float* epi_stage = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
+    float* res_stage = epi_stage + C::EPI_BYTES / 4;   // [8 warps][32 rows][RES_LD] (RES only)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto stage_a = [&](int s) { return smem + s * C::STAGE_BYTES; };
@@ -352,6 +359,59 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         const uint32_t lane_col = ((uint32_t)(quarter * 32) << 16) + half * HALF;
         uint32_t g = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
+            const int img = m_tile / tiles_per_img, rem = m_tile - img * tiles_per_img;
+            const int ho0 = (rem / p.tiles_x) * p.BH, wo0 = (rem % p.tiles_x) * BW;
+            float* stg = epi_stage + (warp - 6) * 32 * C::EPI_LD;
+            // epilogue mapping: LPR lanes cover the CW contiguous channels of one pixel (CW=32: a full 128-byte line per
+            // pixel and store instruction), RPI pixels per instruction, NST instructions per 32-pixel chunk
+            constexpr int CW = C::EPI_CW, LPR = CW / 4, RPI = 32 / LPR, NST = 32 / RPI;
+            const int sub = lane % LPR, rbase = lane / LPR;
+            const int nb = n_tile * BN + half * HALF + sub * 4;               // this lane's first channel in chunk 0
+            const float* __restrict__ rsrc = p.res1 ? p.res1 : p.res2;        // the graphs never use res1 and res2 together
+            const int r_cs = p.res1 ? p.res1_cs : p.res2_cs, r_co = p.res1 ? p.res1_co : p.res2_co;
+            const bool r_pre = p.res1 != nullptr;
+            const float neg_slope = p.act == FCP_ACT_NONE ? 1.f : (p.act == FCP_ACT_RELU ? 0.f : p.slope);
+            // pixel index of staged row (rbase + RPI*st); -1 when the row lies outside the image (tile overshoot)
+            auto row_m = [&](int st, int& ho, int& wo) -> long long {
+                const int prow = quarter * 32 + rbase + RPI * st;
+                ho = ho0 + (prow >> p.bw_log2);
+                wo = wo0 + (prow & (BW - 1));
+                return (ho < p.Ho && wo < p.Wo) ? ((long long)img * p.Ho + ho) * p.Wo + wo : -1;
+            };
+            auto res_pixel = [&](long long m, int ho, int wo) -> long long {   // pixel of the residual operand for output pixel m
+                if (r_pre || !p.res2_h) return m;
+                // nearest resize of the added map (FPN top-down, _layers.py:137-142)
+                const int hs = min((int)floorf(ho * ((float)p.res2_h / (float)p.Ho)), p.res2_h - 1);
+                const int ws = min((int)floorf(wo * ((float)p.res2_w / (float)p.Wo)), p.res2_w - 1);
+                return ((long long)img * p.res2_h + hs) * p.res2_w + ws;
+            };
+            float* rs = res_stage + (warp - 6) * 32 * C::RES_LD;
+            if constexpr (RES) {
+                if (rsrc) {
+                    // stream this warp's residual sub-tile (32 pixels x HALF channels) into shared memory with cp.async while
+                    // the K loop runs: LPR lanes cover the contiguous bytes of one pixel, RPI pixels per instruction
+                    constexpr int RL = HALF / 4, RR = 32 / RL;   // lanes per residual row, rows per instruction
+                    const int col = (lane % RL) * 4;
+                    const int nn = n_tile * BN + half * HALF + col;
+#pragma unroll 4
+                    for (int it = 0; it < 32 / RR; ++it) {
+                        const int row = it * RR + lane / RL;
+                        const int prow = quarter * 32 + row;
+                        const int ho = ho0 + (prow >> p.bw_log2), wo = wo0 + (prow & (BW - 1));
+                        if (ho >= p.Ho || wo >= p.Wo || nn + 3 >= p.Cout) continue;
+                        size_t rp = ((size_t)img * p.Ho + ho) * p.Wo + wo;
+                        if (!r_pre && p.res2_h) {
+                            const int hs = min((int)floorf(ho * ((float)p.res2_h / (float)p.Ho)), p.res2_h - 1);
+                            const int ws = min((int)floorf(wo * ((float)p.res2_w / (float)p.Wo)), p.res2_w - 1);
+                            rp = ((size_t)img * p.res2_h + hs) * p.res2_w + ws;
+                        }
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(rs + row * C::RES_LD + col)),
+                                     "l"(rsrc + rp * r_cs + r_co + nn) : "memory");
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                }
+            }
             float acc[HALF];
 #pragma unroll
             for (int j = 0; j < HALF; ++j) acc[j] = 0.f;
@@ -376,82 +436,63 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             // shared memory turns them into channel-contiguous float4s so that residual loads and output stores are
             // coalesced (4 lanes cover the 64 contiguous bytes of one pixel's 16 channels).  Kept deliberately compact
             // (one activation form, no per-element guards on the fast path): an unrolled epilogue overflowed the I-cache.
-            const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
-            const int img = m_tile / tiles_per_img, rem = m_tile - img * tiles_per_img;
-            const int ho0 = (rem / p.tiles_x) * p.BH, wo0 = (rem % p.tiles_x) * BW;
-            float* stg = epi_stage + (warp - 6) * 32 * C::EPI_LD;
-            const int sub = lane & 3, rbase = lane >> 2;                      // float4 slot within 16 channels, row within 8
-            const int nb = n_tile * BN + half * HALF + sub * 4;               // this lane's first channel in chunk 0
-            const float* __restrict__ rsrc = p.res1 ? p.res1 : p.res2;        // the graphs never use res1 and res2 together
-            const int r_cs = p.res1 ? p.res1_cs : p.res2_cs, r_co = p.res1 ? p.res1_co : p.res2_co;
-            const bool r_pre = p.res1 != nullptr;
-            const float neg_slope = p.act == FCP_ACT_NONE ? 1.f : (p.act == FCP_ACT_RELU ? 0.f : p.slope);
-            float* optr[4];
-            const float* rptr[4];
-            const float* r3ptr[4];
-#pragma unroll
-            for (int st = 0; st < 4; ++st) {
-                const int prow = quarter * 32 + rbase + 8 * st;               // pixel of the 128-pixel box
-                const int ho = ho0 + (prow >> p.bw_log2), wo = wo0 + (prow & (BW - 1));
-                const bool ok = ho < p.Ho && wo < p.Wo;
-                const size_t m = ((size_t)img * p.Ho + ho) * p.Wo + wo;
-                size_t rp = m;
-                if (!r_pre && p.res2_h) {   // nearest resize of the added map (FPN top-down, _layers.py:137-142)
-                    int hs = min((int)floorf(ho * ((float)p.res2_h / (float)p.Ho)), p.res2_h - 1);
-                    int ws = min((int)floorf(wo * ((float)p.res2_w / (float)p.Wo)), p.res2_w - 1);
-                    rp = ((size_t)img * p.res2_h + hs) * p.res2_w + ws;
-                }
-                optr[st] = ok ? p.out + m * p.out_cs + p.out_co + nb : nullptr;
-                rptr[st] = rsrc ? rsrc + rp * r_cs + r_co + nb : nullptr;
-                r3ptr[st] = p.res3 ? p.res3 + m * p.res3_cs + p.res3_co + nb : nullptr;
+            if constexpr (RES) {
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                __syncwarp();
             }
 #pragma unroll
-            for (int c16 = 0; c16 < HALF / 16; ++c16) {
-                const int n = nb + c16 * 16;
+            for (int cc = 0; cc < HALF / CW; ++cc) {
+                const int n = nb + cc * CW;
                 __syncwarp();
 #pragma unroll
-                for (int j = 0; j < 16; j += 4)
+                for (int j = 0; j < CW; j += 4)
                     *reinterpret_cast<float4*>(stg + lane * C::EPI_LD + j) =
-                        make_float4(acc[c16 * 16 + j], acc[c16 * 16 + j + 1], acc[c16 * 16 + j + 2], acc[c16 * 16 + j + 3]);
+                        make_float4(acc[cc * CW + j], acc[cc * CW + j + 1], acc[cc * CW + j + 2], acc[cc * CW + j + 3]);
                 __syncwarp();
                 if (n + 3 < p.Cout) {
                     const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n));
                     const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n));
-                    float4 rv[4];
-#pragma unroll
-                    for (int st = 0; st < 4; ++st)
-                        rv[st] = (rptr[st] && optr[st]) ? __ldg(reinterpret_cast<const float4*>(rptr[st] + c16 * 16)) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                    for (int st = 0; st < 4; ++st) {
-                        if (!optr[st]) continue;
-                        float4 x = *reinterpret_cast<const float4*>(stg + (rbase + 8 * st) * C::EPI_LD + sub * 4);
+#pragma unroll 4
+                    for (int st = 0; st < NST; ++st) {
+                        int ho, wo;
+                        const long long m = row_m(st, ho, wo);
+                        if (m < 0) continue;
+                        float4 x = *reinterpret_cast<const float4*>(stg + (rbase + RPI * st) * C::EPI_LD + sub * 4);
+                        float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (rsrc) {
+                            if constexpr (RES) rv = *reinterpret_cast<const float4*>(rs + (rbase + RPI * st) * C::RES_LD + cc * CW + sub * 4);
+                            else rv = __ldg(reinterpret_cast<const float4*>(rsrc + res_pixel(m, ho, wo) * r_cs + r_co + n));
+                        }
                         x.x = x.x * sc.x + sh.x; x.y = x.y * sc.y + sh.y; x.z = x.z * sc.z + sh.z; x.w = x.w * sc.w + sh.w;
-                        if (r_pre) { x.x += rv[st].x; x.y += rv[st].y; x.z += rv[st].z; x.w += rv[st].w; }
+                        if (r_pre) { x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w; }
                         x.x = x.x > 0.f ? x.x : x.x * neg_slope; x.y = x.y > 0.f ? x.y : x.y * neg_slope;
                         x.z = x.z > 0.f ? x.z : x.z * neg_slope; x.w = x.w > 0.f ? x.w : x.w * neg_slope;
                         x.x *= p.post_scale; x.y *= p.post_scale; x.z *= p.post_scale; x.w *= p.post_scale;
-                        if (!r_pre) { x.x += rv[st].x; x.y += rv[st].y; x.z += rv[st].z; x.w += rv[st].w; }
-                        if (r3ptr[st]) {
-                            const float4 r3 = __ldg(reinterpret_cast<const float4*>(r3ptr[st] + c16 * 16));
+                        if (!r_pre) { x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w; }
+                        if (p.res3) {
+                            const float4 r3 = __ldg(reinterpret_cast<const float4*>(p.res3 + m * p.res3_cs + p.res3_co + n));
                             x.x = x.x * p.post_scale2 + r3.x; x.y = x.y * p.post_scale2 + r3.y;
                             x.z = x.z * p.post_scale2 + r3.z; x.w = x.w * p.post_scale2 + r3.w;
                         }
-                        *reinterpret_cast<float4*>(optr[st] + c16 * 16) = x;
+                        *reinterpret_cast<float4*>(p.out + m * p.out_cs + p.out_co + n) = x;
                     }
                 } else if (n < p.Cout) {
-                    // ragged tail (Cout not a multiple of 4, e.g. the 19-class logits): guarded scalar path
+                    // ragged tail (Cout not a multiple of 4, e.g. the 19-class logits): guarded scalar path, global residual
 #pragma unroll 1
-                    for (int st = 0; st < 4; ++st) {
-                        if (!optr[st]) continue;
+                    for (int st = 0; st < NST; ++st) {
+                        int ho, wo;
+                        const long long m = row_m(st, ho, wo);
+                        if (m < 0) continue;
+                        const long long rp = res_pixel(m, ho, wo);
 #pragma unroll 1
                         for (int e = 0; e < 4 && n + e < p.Cout; ++e) {
-                            float x = stg[(rbase + 8 * st) * C::EPI_LD + sub * 4 + e] * __ldg(p.scale + n + e) + __ldg(p.shift + n + e);
-                            const float rvs = rptr[st] ? rptr[st][c16 * 16 + e] : 0.f;
+                            float x = stg[(rbase + RPI * st) * C::EPI_LD + sub * 4 + e] * __ldg(p.scale + n + e) + __ldg(p.shift + n + e);
+                            const float rvs = rsrc ? rsrc[rp * r_cs + r_co + n + e] : 0.f;
                             if (r_pre) x += rvs;
                             x = (x > 0.f ? x : x * neg_slope) * p.post_scale;
                             if (!r_pre) x += rvs;
-                            if (r3ptr[st]) x = x * p.post_scale2 + r3ptr[st][c16 * 16 + e];
-                            optr[st][c16 * 16 + e] = x;
+                            if (p.res3) x = x * p.post_scale2 + p.res3[m * p.res3_cs + p.res3_co + n + e];
+                            p.out[m * p.out_cs + p.out_co + n + e] = x;
                         }
                     }
                 }
@@ -487,16 +528,16 @@ bool make_map(CUtensorMap* map, void* base, int rank, const cuuint64_t* dims, co
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN>
+template <int BN, bool RES>
 int launch(fcp_ctx* ctx, const TcParams& p) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, RES>;
     static bool configured = false;
     if (!configured) {
-        FCP_CUDA(ctx, cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        FCP_CUDA(ctx, cudaFuncSetAttribute(conv_tc_kernel<BN, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         configured = true;
     }
     int grid = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
-    conv_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, ctx->stream>>>(p);
+    conv_tc_kernel<BN, RES><<<grid, NUM_THREADS, C::SMEM_BYTES, ctx->stream>>>(p);
     FCP_KERNEL_CHECK(ctx);
     return FCP_OK;
 }
@@ -568,17 +609,20 @@ int launch_conv_tc(fcp_ctx* ctx, const ConvOp& op) {
     p.post_scale2 = op.post_scale2; p.res3 = op.res3; p.res3_cs = op.res3_cs; p.res3_co = op.res3_co;
 #ifdef FCP_EXP_TIMELINE
     static int shots = 0;
-    const bool shoot = getenv("FCP_TC_TIMELINE") && wt.k == 3 && wt.cin == 256 && wt.cout == 256 && shots < 1 && p.N * p.Ho * p.Wo >= 65536;
+    const bool shoot = getenv("FCP_TC_TIMELINE") && wt.k == 3 && wt.cin == 256 && wt.cout == 256 && shots < (getenv("FCP_TL_SHOT") ? atoi(getenv("FCP_TL_SHOT")) + 1 : 1) && p.N * p.Ho * p.Wo >= 65536;
     long long* dbg = nullptr;
     if (shoot) { cudaMalloc(&dbg, 512 * 16 * 8); cudaMemset(dbg, 0, 512 * 16 * 8); p.dbg = dbg; ++shots; }
-    int rc = BN == 128 ? launch<128>(ctx, p) : (BN == 64 ? launch<64>(ctx, p) : launch<32>(ctx, p));
-    if (shoot) {
+    const bool print_it = shoot && shots == (getenv("FCP_TL_SHOT") ? atoi(getenv("FCP_TL_SHOT")) + 1 : 1);
+    int rc = BN == 128 ? launch<128, false>(ctx, p) : (BN == 64 ? launch<64, false>(ctx, p) : launch<32, false>(ctx, p));
+    if (shoot && !print_it) cudaFree(dbg);
+    if (print_it) {
         cudaStreamSynchronize(ctx->stream);
         std::vector<long long> h(512 * 16);
         cudaMemcpy(h.data(), dbg, 512 * 16 * 8, cudaMemcpyDeviceToHost);
-        long long t0 = h[100 * 16 + 0];
+        long long t0 = h[(getenv("FCP_TL_G0") ? atoi(getenv("FCP_TL_G0")) : 100) * 16 + 0];
+        fprintf(stderr, "[timeline] res1=%p res2=%p tiles=%d\n", (void*)p.res1, (void*)p.res2, p.num_tiles);
         fprintf(stderr, "[timeline] g: prod_wait_empty prod_issued | mma_dempty mma_conv mma_issued | conv_full conv_done | drain_dfull drain_done\n");
-        for (int g = 100; g < 124; ++g) {
+        for (int g = (getenv("FCP_TL_G0") ? atoi(getenv("FCP_TL_G0")) : 100); g < (getenv("FCP_TL_G0") ? atoi(getenv("FCP_TL_G0")) : 100) + 24; ++g) {
             fprintf(stderr, "[timeline] %3d:", g);
             for (int e = 0; e < 9; ++e) fprintf(stderr, " %7lld", h[g * 16 + e] ? h[g * 16 + e] - t0 : -1);
             fprintf(stderr, "\n");
@@ -587,9 +631,16 @@ int launch_conv_tc(fcp_ctx* ctx, const ConvOp& op) {
     }
     return rc;
 #endif
-    if (BN == 128) return launch<128>(ctx, p);
-    if (BN == 64) return launch<64>(ctx, p);
-    return launch<32>(ctx, p);
+    // residual-staging variant: tiles with a residual operand and a short K loop (their epilogue would otherwise wait on HBM)
+    const bool res = (op.res1 || op.res2) && wt.cout % 4 == 0 && getenv("FCP_TC_NO_RES") == nullptr;
+    if (res) {
+        if (BN == 128) return launch<128, true>(ctx, p);
+        if (BN == 64) return launch<64, true>(ctx, p);
+        return launch<32, true>(ctx, p);
+    }
+    if (BN == 128) return launch<128, false>(ctx, p);
+    if (BN == 64) return launch<64, false>(ctx, p);
+    return launch<32, false>(ctx, p);
 }
 
 }  // namespace fcp
