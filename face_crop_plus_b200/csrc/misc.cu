@@ -35,21 +35,52 @@ __global__ void __launch_bounds__(256, 1) stem7_kernel(const void* __restrict__ 
     for (int i = tid; i < 147 * 64 / 4; i += 256)
         reinterpret_cast<float4*>(sw)[i] = reinterpret_cast<const float4*>(wkn)[i];
     const int hi0 = ho0 * 2 - 3, wi0 = wo0 * 2 - 3;
+    // Stage the raw input rows first (coalesced 32-bit words, 8 independent loads in flight per thread), then scatter them
+    // into the three channel planes from shared memory: a per-element global load loop here was latency-bound and
+    // cost ~40% of the kernel.
+    uint32_t* raw = reinterpret_cast<uint32_t*>(sp + 3 * ST_PH * ST_LD);      // [ST_PH][RAW_WORDS]
+    constexpr int ELT = MODE == 0 ? 1 : 4;                                     // bytes per input element
+    constexpr int RAW_WORDS = (ST_PW * 3 * ELT + 3) / 4 + 2;                   // words per staged row (+ alignment slack)
+    const char* base = static_cast<const char*>(src);
+    const long long img_bytes = (long long)H * W * 3 * ELT, total_bytes = (long long)N * img_bytes;
+    for (int i0 = tid; i0 < ST_PH * RAW_WORDS; i0 += 256 * 8) {
+        uint32_t v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * 256;
+            v[u] = 0;
+            if (i < ST_PH * RAW_WORDS) {
+                const int py = i / RAW_WORDS, wd = i - py * RAW_WORDS;
+                const int hi = hi0 + py;
+                // byte address of the first element of the row segment, aligned down to 4
+                const long long row0 = (long long)n * img_bytes + ((long long)hi * W + wi0) * 3 * ELT;
+                const long long a = (row0 & ~3LL) + 4LL * wd;
+                if (hi >= 0 && hi < H && a >= 0 && a + 4 <= total_bytes) v[u] = *reinterpret_cast<const uint32_t*>(base + a);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * 256;
+            if (i < ST_PH * RAW_WORDS) raw[i] = v[u];
+        }
+    }
+    __syncthreads();
     for (int i = tid; i < ST_PH * ST_PW * 3; i += 256) {
-        int c = i % 3;
-        int t = i / 3;
-        int px = t % ST_PW, py = t / ST_PW;
-        int hi = hi0 + py, wi = wi0 + px;
+        const int c = i % 3;
+        const int t = i / 3;
+        const int px = t % ST_PW, py = t / ST_PW;
+        const int hi = hi0 + py, wi = wi0 + px;
         float v = 0.f;
         if (hi >= 0 && hi < H && wi >= 0 && wi < W) {
-            size_t pix = ((size_t)n * H + hi) * W + wi;
+            const long long row0 = (long long)n * img_bytes + ((long long)hi * W + wi0) * 3 * ELT;
+            const int mis = (int)(row0 & 3);                                   // the staged row starts `mis` bytes early
             if (MODE == 0) {
                 // RGB uint8 -> BGR, minus (104,117,123): retinaface.py:450-451
-                const uint8_t* s8 = static_cast<const uint8_t*>(src);
+                const uint8_t* rb = reinterpret_cast<const uint8_t*>(raw + py * RAW_WORDS);
                 const float mean = c == 0 ? 104.f : (c == 1 ? 117.f : 123.f);
-                v = (float)s8[pix * 3 + (2 - c)] - mean;
+                v = (float)rb[mis + px * 3 + (2 - c)] - mean;
             } else {
-                v = static_cast<const float*>(src)[pix * 3 + c];
+                v = reinterpret_cast<const float*>(raw + py * RAW_WORDS)[px * 3 + c];   // float rows are 4-byte aligned: mis == 0
             }
         }
         sp[(c * ST_PH + py) * ST_LD + px] = v;
@@ -266,7 +297,8 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, int HW, int C,
 
 int launch_stem7(fcp_ctx* ctx, const void* src, int mode, int n, int h, int w, const float* w_kn, const float* scale,
                  const float* shift, Tensor out) {
-    size_t smem = (147 * 64 + 3 * ST_PH * ST_LD) * sizeof(float);
+    // weights + 3 channel planes + raw row staging (mode 1 rows are floats: ST_PW*3 words)
+    size_t smem = (147 * 64 + 3 * ST_PH * ST_LD + ST_PH * (ST_PW * 3 + 3)) * sizeof(float);
     static bool configured = false;
     if (!configured) {
         FCP_CUDA(ctx, cudaFuncSetAttribute(stem7_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
