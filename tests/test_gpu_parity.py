@@ -321,3 +321,47 @@ def test_enhance_forward_64x64_and_linearity_property(enh_ctx):
     a = full[:, :, 4 * 16 + 160:4 * 112 - 160, 4 * 24 + 160:4 * 136 - 160]
     b = crop[:, :, 160:-160, 160:-160]
     assert a.shape == b.shape and np.abs(a - b).max() < 5e-3
+
+
+# ------------------------------------------------------------------------------------------ full-size (1024x1024)
+def test_detect_full_size_vs_oracle(ctx):
+    """BASELINE.json's image size: 2 images of 1024x1024 (43 008 priors each) against the oracle."""
+    from face_crop_plus_b200 import _abi
+    from oracle import pipeline
+    sd = synth.make_state_dict("retinaface", 0, class_bias=4.8)       # the bench's candidate density
+    ctx.load_state_dict(_abi.MODEL_RETINAFACE, sd)
+    imgs = synth.make_images(2, 1024, 1024, seed=1234)
+    for strategy in ("all", "largest"):
+        lms, idx, anchors, boxes = pipeline.detect(imgs, sd, 0.6, 0.4, strategy)
+        out = ctx.detect(imgs, 0.6, 0.4, strategy)
+        got = list(zip(out["indices"].tolist(), out["anchors"].tolist()))
+        ref = list(zip(idx, anchors))
+        assert sorted(got) == sorted(ref) and out["indices"].tolist() == idx       # same priors selected per image
+        # within an image faces are ordered by score; 200+ random faces contain scores that differ by < 1e-6 (float32
+        # spacing near 1.0 is 6e-8), so the order may differ only between such near-ties
+        pos = {k: j for j, k in enumerate(got)}
+        for j, k in enumerate(ref):
+            if pos[k] != j:
+                assert abs(float(out["scores"][pos[k]]) - float(out["scores"][j])) < 1e-5
+            assert np.abs(out["landmarks"][pos[k]] - lms[j]).max() < TOL
+    assert len(idx) == 2
+    ctx.load_state_dict(_abi.MODEL_RETINAFACE, synth.make_state_dict("retinaface", 0, class_bias=CLASS_BIAS))
+
+
+def test_full_size_batch_consistency_between_conv_kernels(det_ctx, par_ctx):
+    """Size-independent property at the bench shape (1024x1024, 24 images, ragged micro-batches): the tensor-core
+    (3xTF32) and the CUDA-core (fp32) convolution paths must select the same priors and agree to the float tolerance."""
+    imgs = synth.make_images(24, 1024, 1024, seed=4000)
+    tgt = landmarks_target((256, 256), 0.65)
+    res = {}
+    for impl in (1, 0):
+        det_ctx.set_conv_impl(impl)
+        det_ctx.set_micro_batch(16 if impl else 5, 32 if impl else 7)
+        res[impl] = det_ctx.pipeline(imgs, None, tgt, (256, 256), 0.6, 0.4, "largest")
+    det_ctx.set_conv_impl(1)
+    det_ctx.set_micro_batch(16, 32)
+    a, b = res[1], res[0]
+    assert a["count"] == b["count"] > 0 and a["indices"].tolist() == b["indices"].tolist()
+    assert np.abs(a["landmarks"] - b["landmarks"]).max() < TOL
+    assert (a["crops"] != b["crops"]).mean() < 0.02 and (a["labels"] != b["labels"]).mean() < 5e-3
+    assert np.array_equal(a["hist"].sum(1), np.full(a["count"], 256 * 256))
