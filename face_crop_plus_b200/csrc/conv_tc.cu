@@ -62,6 +62,7 @@ struct alignas(64) TcParams {
     int act; float slope;
     float post_scale; const float* res2; int res2_cs, res2_co, res2_h, res2_w;
     float post_scale2; const float* res3; int res3_cs, res3_co;
+    int exp_nolo;                              // experiment: skip the w_lo loads (wrong results; L2-traffic probe)
     long long* dbg;                            // FCP_EXP_TIMELINE: clock64 stamps of CTA 0, [g][16]
 };
 
@@ -108,8 +109,21 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
     return v;
 }
-__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+// explicit shared-space float4 accesses: through a generic pointer the compiler emits LD.E/ST.E (generic path) for
+// the epilogue slab, which measured ~4x slower than LDS/STS
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f4(uint32_t addr, const float4& v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts_f1(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ float lds_f1(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
 }
 #ifdef FCP_EXP_TIMELINE
 #define TL(g, ev) do { if (p.dbg && blockIdx.x == 0 && (g) < 512) p.dbg[(g) * 16 + (ev)] = clock64(); } while (0)
@@ -187,28 +201,30 @@ __device__ __forceinline__ float act_fn(float v, int act, float slope) {
     return v;
 }
 
-// RES: the tile's residual operand (bottleneck shortcut / FPN / RRDB skip) is prefetched with cp.async into shared
-// memory while the K loop runs, so the epilogue never waits on HBM; it costs pipeline stages (shared-memory budget).
-template <int BN, bool RES> struct Cfg {
+// One shared-memory slab per epilogue warp, S[32 pixels][BN/2 channels (+4 pad)], serves three purposes in turn: the
+// tile's residual operand (bottleneck shortcut / FPN top-down / RRDB skip) is prefetched into it with cp.async while the
+// K loop runs; the fused epilogue math then runs in place, pixel-per-thread (the TMEM lane layout); finally the slab is
+// read back transposed (channel-contiguous float4s) so that the output stores are full 128-byte lines.
+template <int BN> struct Cfg {
     static constexpr int B_TILE_BYTES = BN * KB * 4;
     static constexpr int STAGE_BYTES = A_TILE_BYTES + 2 * B_TILE_BYTES;   // fp32 A tile + w_hi + w_lo
-    static constexpr int STAGES = RES ? (BN >= 128 ? 2 : (BN == 64 ? 4 : 6)) : (BN >= 128 ? 3 : (BN == 64 ? 5 : 7));
+    static constexpr int STAGES = BN >= 128 ? 3 : (BN == 64 ? 5 : 7);
     // tensor memory: [0, 2*BN) two partial-sum buffers; then STAGES x (a_hi 32 cols | a_lo 32 cols)
     static constexpr int TMEM_A0 = 2 * BN;
     static constexpr int TMEM_COLS = 512;
     static_assert(TMEM_A0 + STAGES * 64 <= TMEM_COLS, "tensor memory budget");
-    static constexpr int EPI_CW = BN >= 64 ? 32 : 16;                     // channels per epilogue chunk (32 -> full 128-byte lines)
-    static constexpr int EPI_LD = EPI_CW + 4;                             // floats per staged row (+4 pad: conflict-free float4s)
-    static constexpr int EPI_BYTES = 8 * 32 * EPI_LD * 4;                 // 8 epilogue warps x 32 pixels x EPI_CW channels
-    static constexpr int RES_LD = BN / 2 + 4;                             // residual rows: BN/2 channels + pad
-    static constexpr int RES_BYTES = RES ? 8 * 32 * RES_LD * 4 : 0;       // 8 epilogue warps x 32 pixels x BN/2 channels
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES + RES_BYTES;
+    static constexpr int HALF = BN / 2;                                   // channels owned by one epilogue warp
+    static constexpr int EPI_CW = HALF >= 32 ? 32 : 16;                   // channels per store chunk (32 -> full 128-byte lines)
+    static constexpr int S_LD = HALF + 4;                                 // floats per slab row (+4 pad: conflict-free float4s)
+    static constexpr int S_BYTES = 8 * 32 * S_LD * 4;                     // 8 epilogue warps x 32 pixels
+    static constexpr int PAR_BYTES = 8 * 2 * HALF * 4;                    // per warp: scale[HALF] | shift[HALF]
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + S_BYTES + PAR_BYTES;
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
-template <int BN, bool RES>
+template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
-    using C = Cfg<BN, RES>;
+    using C = Cfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -218,8 +234,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     uint64_t* d_full = bars + 3 * C::STAGES;       // [2]  partial sum of one K-block is complete in TMEM buffer b
     uint64_t* d_empty = d_full + 2;                // [2]  buffer b has been drained to registers
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(d_empty + 2);
-    float* epi_stage = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
-    float* res_stage = epi_stage + C::EPI_BYTES / 4;   // [8 warps][32 rows][RES_LD] (RES only)
+    float* slab_all = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);   // [8 warps][32 rows][S_LD]
+    float* par_all = slab_all + C::S_BYTES / 4;                                            // [8 warps][2][HALF]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto stage_a = [&](int s) { return smem + s * C::STAGE_BYTES; };
@@ -250,22 +266,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
                 const int img = m_tile / tiles_per_img, rem = m_tile - img * tiles_per_img;
                 const int ho0 = (rem / p.tiles_x) * p.BH, wo0 = (rem % p.tiles_x) * BW;
+                int tap = 0, cc = 0, r = 0, sx = 0;                          // K-block = (tap (r, sx), 32-channel chunk cc)
                 for (int kb = 0; kb < kblocks; ++kb) {
-                    const int tap = kb / cchunks, c0 = (kb - tap * cchunks) * KB;
-                    const int r = tap / p.KW, s = tap - r * p.KW;
-                    mbar_wait<true>(&empty[stage], phase ^ 1);
-                    TL(gp, 0);
-                    mbar_expect_tx(&full[stage], A_TILE_BYTES + 2 * C::B_TILE_BYTES);
-                    int dy = r - p.pad, dx = s - p.pad, map = 0;
+                    int dy = r - p.pad, dx = sx - p.pad, map = 0;
                     if (p.stride == 2) {   // input row 2*ho + dy lives in parity view (dy & 1) at row ho + (dy - (dy & 1)) / 2
                         const int py = dy & 1, px = dx & 1;
                         map = py * 2 + px;
                         dy = (dy - py) >> 1;
                         dx = (dx - px) >> 1;
                     }
+                    const int c0 = cc * KB, kcol = tap * p.Cin + c0;
+                    mbar_wait<true>(&empty[stage], phase ^ 1);
+                    TL(gp, 0);
+                    mbar_expect_tx(&full[stage], A_TILE_BYTES + ((p.exp_nolo & 1) ? 1 : 2) * C::B_TILE_BYTES);
                     tma_load_4d(stage_a(stage), &p.tmA[map], &full[stage], c0, wo0 + dx, ho0 + dy, img);
-                    tma_load_2d(stage_b_hi(stage), &p.tmBhi, &full[stage], tap * p.Cin + c0, n_tile * BN);
-                    tma_load_2d(stage_b_lo(stage), &p.tmBlo, &full[stage], tap * p.Cin + c0, n_tile * BN);
+                    tma_load_2d(stage_b_hi(stage), &p.tmBhi, &full[stage], kcol, n_tile * BN);
+                    if (!(p.exp_nolo & 1)) tma_load_2d(stage_b_lo(stage), &p.tmBlo, &full[stage], kcol, n_tile * BN);
+                    if (++cc == cchunks) { cc = 0; ++tap; if (++sx == p.KW) { sx = 0; ++r; } }
                     TL(gp, 1); ++gp;
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -286,9 +303,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 for (int kb = 0; kb < kblocks; ++kb, ++g) {
                     if (g % NUM_ISSUERS == me) {
                         const uint32_t buf = g & 1;
-                        mbar_wait(&d_empty[buf], ((g >> 1) & 1) ^ 1);         // partial-sum buffer drained
+                        if (p.exp_nolo & 16) mbar_wait<true>(&d_empty[buf], ((g >> 1) & 1) ^ 1);
+                        else mbar_wait(&d_empty[buf], ((g >> 1) & 1) ^ 1);    // partial-sum buffer drained
                         TL(g, 2);
-                        mbar_wait(&conv[stage], phase);                       // operands (hi/lo) ready
+                        if (p.exp_nolo & 16) mbar_wait<true>(&conv[stage], phase);
+                        else mbar_wait(&conv[stage], phase);                  // operands (hi/lo) ready
                         TL(g, 3);
                         tc_fence_after();
                         const uint32_t d_tmem = tmem_base + buf * BN;
@@ -350,71 +369,62 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         }
     } else if (warp < 14) {
         // ============================================================ accumulate + epilogue (warps 6..13, 256 threads)
-        constexpr int HALF = BN / 2;                                          // columns owned by this warp
+        constexpr int HALF = C::HALF;                                         // columns owned by this warp
         constexpr int CH = HALF >= 32 ? 32 : 16;                              // columns per tcgen05.ld
         constexpr int NCH = HALF / CH;
+        constexpr int LD = C::S_LD;
         const int quarter = warp & 3;                                         // TMEM lanes [32*quarter, 32*quarter+32)
         const int half = (warp - 6) >> 2;
-        const int pix = quarter * 32 + lane;                                  // row of the tile == pixel of the box
         const uint32_t lane_col = ((uint32_t)(quarter * 32) << 16) + half * HALF;
+        const uint32_t S = smem_u32(slab_all + (warp - 6) * 32 * LD);         // this warp's slab [32][LD] (shared-space address)
+        const uint32_t par = smem_u32(par_all + (warp - 6) * 2 * HALF);       // scale[HALF] | shift[HALF]
+        // store mapping: LPR lanes cover the CW contiguous channels of one pixel (CW=32: a full 128-byte line per pixel and
+        // store instruction), RPI pixels per instruction, NST instructions per 32-pixel chunk
+        constexpr int CW = C::EPI_CW, LPR = CW / 4, RPI = 32 / LPR, NST = 32 / RPI;
+        const int sub = lane % LPR, rbase = lane / LPR;
+        // residual prefetch mapping: RL lanes cover the HALF contiguous channels of one pixel, RR pixels per instruction
+        constexpr int RL = HALF / 4, RR = 32 / RL;
+        const int rcol = (lane % RL) * 4, rrow = lane / RL;
+        const float* __restrict__ rsrc = p.res1 ? p.res1 : p.res2;            // the graphs never use res1 and res2 together
+        const int r_cs = p.res1 ? p.res1_cs : p.res2_cs, r_co = p.res1 ? p.res1_co : p.res2_co;
+        const bool r_pre = p.res1 != nullptr, r_post = !r_pre && rsrc != nullptr;
+        const bool r_resize = !r_pre && p.res2_h != 0;                        // nearest resize of the added map (_layers.py:137-142)
+        const float rs_y = r_resize ? (float)p.res2_h / (float)p.Ho : 1.f, rs_x = r_resize ? (float)p.res2_w / (float)p.Wo : 1.f;
+        const float neg_slope = p.act == FCP_ACT_NONE ? 1.f : (p.act == FCP_ACT_RELU ? 0.f : p.slope);
+        const float post_scale = p.post_scale;
         uint32_t g = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
             const int img = m_tile / tiles_per_img, rem = m_tile - img * tiles_per_img;
             const int ho0 = (rem / p.tiles_x) * p.BH, wo0 = (rem % p.tiles_x) * BW;
-            float* stg = epi_stage + (warp - 6) * 32 * C::EPI_LD;
-            // epilogue mapping: LPR lanes cover the CW contiguous channels of one pixel (CW=32: a full 128-byte line per
-            // pixel and store instruction), RPI pixels per instruction, NST instructions per 32-pixel chunk
-            constexpr int CW = C::EPI_CW, LPR = CW / 4, RPI = 32 / LPR, NST = 32 / RPI;
-            const int sub = lane % LPR, rbase = lane / LPR;
-            const int nb = n_tile * BN + half * HALF + sub * 4;               // this lane's first channel in chunk 0
-            const float* __restrict__ rsrc = p.res1 ? p.res1 : p.res2;        // the graphs never use res1 and res2 together
-            const int r_cs = p.res1 ? p.res1_cs : p.res2_cs, r_co = p.res1 ? p.res1_co : p.res2_co;
-            const bool r_pre = p.res1 != nullptr;
-            const float neg_slope = p.act == FCP_ACT_NONE ? 1.f : (p.act == FCP_ACT_RELU ? 0.f : p.slope);
-            // pixel index of staged row (rbase + RPI*st); -1 when the row lies outside the image (tile overshoot)
-            auto row_m = [&](int st, int& ho, int& wo) -> long long {
-                const int prow = quarter * 32 + rbase + RPI * st;
-                ho = ho0 + (prow >> p.bw_log2);
-                wo = wo0 + (prow & (BW - 1));
-                return (ho < p.Ho && wo < p.Wo) ? ((long long)img * p.Ho + ho) * p.Wo + wo : -1;
-            };
-            auto res_pixel = [&](long long m, int ho, int wo) -> long long {   // pixel of the residual operand for output pixel m
-                if (r_pre || !p.res2_h) return m;
-                // nearest resize of the added map (FPN top-down, _layers.py:137-142)
-                const int hs = min((int)floorf(ho * ((float)p.res2_h / (float)p.Ho)), p.res2_h - 1);
-                const int ws = min((int)floorf(wo * ((float)p.res2_w / (float)p.Wo)), p.res2_w - 1);
-                return ((long long)img * p.res2_h + hs) * p.res2_w + ws;
-            };
-            float* rs = res_stage + (warp - 6) * 32 * C::RES_LD;
-            if constexpr (RES) {
-                if (rsrc) {
-                    // stream this warp's residual sub-tile (32 pixels x HALF channels) into shared memory with cp.async while
-                    // the K loop runs: LPR lanes cover the contiguous bytes of one pixel, RPI pixels per instruction
-                    constexpr int RL = HALF / 4, RR = 32 / RL;   // lanes per residual row, rows per instruction
-                    const int col = (lane % RL) * 4;
-                    const int nn = n_tile * BN + half * HALF + col;
-#pragma unroll 4
-                    for (int it = 0; it < 32 / RR; ++it) {
-                        const int row = it * RR + lane / RL;
-                        const int prow = quarter * 32 + row;
-                        const int ho = ho0 + (prow >> p.bw_log2), wo = wo0 + (prow & (BW - 1));
-                        if (ho >= p.Ho || wo >= p.Wo || nn + 3 >= p.Cout) continue;
-                        size_t rp = ((size_t)img * p.Ho + ho) * p.Wo + wo;
-                        if (!r_pre && p.res2_h) {
-                            const int hs = min((int)floorf(ho * ((float)p.res2_h / (float)p.Ho)), p.res2_h - 1);
-                            const int ws = min((int)floorf(wo * ((float)p.res2_w / (float)p.Wo)), p.res2_w - 1);
-                            rp = ((size_t)img * p.res2_h + hs) * p.res2_w + ws;
-                        }
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(rs + row * C::RES_LD + col)),
-                                     "l"(rsrc + rp * r_cs + r_co + nn) : "memory");
+            const int n0 = n_tile * BN + half * HALF;                         // first channel of this warp
+            const int img_pix0 = img * p.Ho * p.Wo;
+            // ---- this warp's folded-BN scale/shift into shared memory (arrays are padded to cout_pad >= n0 + HALF)
+            for (int j = lane; j < HALF; j += 32) {
+                sts_f1(par + 4 * j, __ldg(p.scale + n0 + j));
+                sts_f1(par + 4 * (HALF + j), __ldg(p.shift + n0 + j));
+            }
+            // ---- residual sub-tile (32 pixels x HALF channels) streams into the slab while the K loop runs
+            if (rsrc && !(p.exp_nolo & 8)) {
+#pragma unroll 2
+                for (int it = 0; it < 32 / RR; ++it) {
+                    const int row = it * RR + rrow, prow = quarter * 32 + row;
+                    const int ho = ho0 + (prow >> p.bw_log2), wo = wo0 + (prow & (BW - 1));
+                    if (ho >= p.Ho || wo >= p.Wo || n0 + rcol + 3 >= p.Cout) continue;
+                    int rp = img_pix0 + ho * p.Wo + wo;
+                    if (r_resize) {
+                        const int hs = min((int)floorf(ho * rs_y), p.res2_h - 1), ws = min((int)floorf(wo * rs_x), p.res2_w - 1);
+                        rp = (img * p.res2_h + hs) * p.res2_w + ws;
                     }
-                    asm volatile("cp.async.commit_group;" ::: "memory");
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(S + 4 * (row * LD + rcol)),
+                                 "l"(rsrc + (size_t)rp * r_cs + r_co + n0 + rcol) : "memory");
                 }
+                asm volatile("cp.async.commit_group;" ::: "memory");
             }
             float acc[HALF];
 #pragma unroll
             for (int j = 0; j < HALF; ++j) acc[j] = 0.f;
+            if (warp == 6 && lane == 0) TL(g, 13);                            // tile prologue (params, residual prefetch) issued
             for (int kb = 0; kb < kblocks; ++kb, ++g) {
                 const uint32_t buf = g & 1;
                 mbar_wait<true>(&d_full[buf], (g >> 1) & 1);
@@ -432,71 +442,76 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 if (lane == 0) mbar_arrive(&d_empty[buf]);
                 if (warp == 6 && lane == 0) TL(g, 8);
             }
-            // ---- fused epilogue.  The accumulators are pixel-per-thread (TMEM lane == thread); a 32x16 transpose through
-            // shared memory turns them into channel-contiguous float4s so that residual loads and output stores are
-            // coalesced (4 lanes cover the 64 contiguous bytes of one pixel's 16 channels).  Kept deliberately compact
-            // (one activation form, no per-element guards on the fast path): an unrolled epilogue overflowed the I-cache.
-            if constexpr (RES) {
-                asm volatile("cp.async.wait_all;" ::: "memory");
-                __syncwarp();
+            // ---- fused epilogue, phase 1 (pixel per thread == TMEM lane, in place in the slab):
+            //      y = post_scale * act(acc * scale + shift [+ res1]) [+ res2]
+            if (rsrc) asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncwarp();
+            if (warp == 6 && lane == 0) TL(g - 1, 10);
+            if (!(p.exp_nolo & 4)) {
+                const uint32_t row = S + 4 * lane * LD;
+#pragma unroll
+                for (int j = 0; j < HALF; j += 4) {
+                    const float4 sc = lds_f4(par + 4 * j);
+                    const float4 sh = lds_f4(par + 4 * (HALF + j));
+                    float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (rsrc) rv = lds_f4(row + 4 * j);
+                    float4 x;
+                    x.x = acc[j] * sc.x + sh.x; x.y = acc[j + 1] * sc.y + sh.y; x.z = acc[j + 2] * sc.z + sh.z; x.w = acc[j + 3] * sc.w + sh.w;
+                    if (r_pre) { x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w; }
+                    x.x = x.x > 0.f ? x.x : x.x * neg_slope; x.y = x.y > 0.f ? x.y : x.y * neg_slope;
+                    x.z = x.z > 0.f ? x.z : x.z * neg_slope; x.w = x.w > 0.f ? x.w : x.w * neg_slope;
+                    x.x *= post_scale; x.y *= post_scale; x.z *= post_scale; x.w *= post_scale;
+                    if (r_post) { x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w; }
+                    sts_f4(row + 4 * j, x);
+                }
             }
-#pragma unroll
+            __syncwarp();
+            if (warp == 6 && lane == 0) TL(g - 1, 11);
+            // ---- phase 2: read the slab back channel-contiguous; coalesced float4 stores (+ the RRDB second residual)
+            auto out_pixel = [&](int st) -> int {                             // output pixel of staged row rbase + RPI*st, -1 = outside
+                const int prow = quarter * 32 + rbase + RPI * st;
+                const int ho = ho0 + (prow >> p.bw_log2), wo = wo0 + (prow & (BW - 1));
+                return (ho < p.Ho && wo < p.Wo) ? img_pix0 + ho * p.Wo + wo : -1;
+            };
+            if (warp == 6 && lane == 0) TL(g - 1, 12);
+            // rolled loops on purpose: the epilogue runs once per tile, and straight-line code that does not fit the
+            // instruction caches is paced by instruction fetch (measured), not by the memory system
+            const bool has3 = p.res3 != nullptr;
+#pragma unroll 1
             for (int cc = 0; cc < HALF / CW; ++cc) {
-                const int n = nb + cc * CW;
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < CW; j += 4)
-                    *reinterpret_cast<float4*>(stg + lane * C::EPI_LD + j) =
-                        make_float4(acc[cc * CW + j], acc[cc * CW + j + 1], acc[cc * CW + j + 2], acc[cc * CW + j + 3]);
-                __syncwarp();
+                const int cl = cc * CW + sub * 4, n = n0 + cl;                // channel within the slab / within the tensor
                 if (n + 3 < p.Cout) {
-                    const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n));
-                    const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n));
-#pragma unroll 4
+                    float* const outp = p.out + p.out_co + n;
+                    const float* const r3p = p.res3 + p.res3_co + n;
+#pragma unroll 2
                     for (int st = 0; st < NST; ++st) {
-                        int ho, wo;
-                        const long long m = row_m(st, ho, wo);
+                        const int m = out_pixel(st);
                         if (m < 0) continue;
-                        float4 x = *reinterpret_cast<const float4*>(stg + (rbase + RPI * st) * C::EPI_LD + sub * 4);
-                        float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (rsrc) {
-                            if constexpr (RES) rv = *reinterpret_cast<const float4*>(rs + (rbase + RPI * st) * C::RES_LD + cc * CW + sub * 4);
-                            else rv = __ldg(reinterpret_cast<const float4*>(rsrc + res_pixel(m, ho, wo) * r_cs + r_co + n));
-                        }
-                        x.x = x.x * sc.x + sh.x; x.y = x.y * sc.y + sh.y; x.z = x.z * sc.z + sh.z; x.w = x.w * sc.w + sh.w;
-                        if (r_pre) { x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w; }
-                        x.x = x.x > 0.f ? x.x : x.x * neg_slope; x.y = x.y > 0.f ? x.y : x.y * neg_slope;
-                        x.z = x.z > 0.f ? x.z : x.z * neg_slope; x.w = x.w > 0.f ? x.w : x.w * neg_slope;
-                        x.x *= p.post_scale; x.y *= p.post_scale; x.z *= p.post_scale; x.w *= p.post_scale;
-                        if (!r_pre) { x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w; }
-                        if (p.res3) {
-                            const float4 r3 = __ldg(reinterpret_cast<const float4*>(p.res3 + m * p.res3_cs + p.res3_co + n));
+                        float4 x = lds_f4(S + 4 * ((rbase + RPI * st) * LD + cl));
+                        if (has3) {
+                            const float4 r3 = __ldg(reinterpret_cast<const float4*>(r3p + (size_t)m * p.res3_cs));
                             x.x = x.x * p.post_scale2 + r3.x; x.y = x.y * p.post_scale2 + r3.y;
                             x.z = x.z * p.post_scale2 + r3.z; x.w = x.w * p.post_scale2 + r3.w;
                         }
-                        *reinterpret_cast<float4*>(p.out + m * p.out_cs + p.out_co + n) = x;
+                        if (!(p.exp_nolo & 2)) *reinterpret_cast<float4*>(outp + (size_t)m * p.out_cs) = x;
                     }
                 } else if (n < p.Cout) {
-                    // ragged tail (Cout not a multiple of 4, e.g. the 19-class logits): guarded scalar path, global residual
+                    // ragged tail (Cout not a multiple of 4, e.g. the 19-class logits; never carries a residual): scalar stores
 #pragma unroll 1
                     for (int st = 0; st < NST; ++st) {
-                        int ho, wo;
-                        const long long m = row_m(st, ho, wo);
+                        const int m = out_pixel(st);
                         if (m < 0) continue;
-                        const long long rp = res_pixel(m, ho, wo);
 #pragma unroll 1
                         for (int e = 0; e < 4 && n + e < p.Cout; ++e) {
-                            float x = stg[(rbase + RPI * st) * C::EPI_LD + sub * 4 + e] * __ldg(p.scale + n + e) + __ldg(p.shift + n + e);
-                            const float rvs = rsrc ? rsrc[rp * r_cs + r_co + n + e] : 0.f;
-                            if (r_pre) x += rvs;
-                            x = (x > 0.f ? x : x * neg_slope) * p.post_scale;
-                            if (!r_pre) x += rvs;
-                            if (p.res3) x = x * p.post_scale2 + p.res3[m * p.res3_cs + p.res3_co + n + e];
-                            p.out[m * p.out_cs + p.out_co + n + e] = x;
+                            float x = lds_f1(S + 4 * ((rbase + RPI * st) * LD + cl + e));
+                            if (p.res3) x = x * p.post_scale2 + p.res3[(size_t)m * p.res3_cs + p.res3_co + n + e];
+                            p.out[(size_t)m * p.out_cs + p.out_co + n + e] = x;
                         }
                     }
                 }
             }
+            __syncwarp();                                                     // slab + params are rewritten by the next tile
+            if (warp == 6 && lane == 0) TL(g - 1, 9);                        // epilogue of this tile finished
         }
     }
     tc_fence_before();
@@ -528,16 +543,16 @@ bool make_map(CUtensorMap* map, void* base, int rank, const cuuint64_t* dims, co
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN, bool RES>
+template <int BN>
 int launch(fcp_ctx* ctx, const TcParams& p) {
-    using C = Cfg<BN, RES>;
+    using C = Cfg<BN>;
     static bool configured = false;
     if (!configured) {
-        FCP_CUDA(ctx, cudaFuncSetAttribute(conv_tc_kernel<BN, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        FCP_CUDA(ctx, cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         configured = true;
     }
     int grid = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
-    conv_tc_kernel<BN, RES><<<grid, NUM_THREADS, C::SMEM_BYTES, ctx->stream>>>(p);
+    conv_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, ctx->stream>>>(p);
     FCP_KERNEL_CHECK(ctx);
     return FCP_OK;
 }
@@ -551,7 +566,9 @@ bool conv_tc_supported(const ConvOp& op) {
     if (op.stride == 2 && !(wt.k == 1 || wt.k == 3)) return false;
     if ((op.in.cs | op.in.co) & 3) return false;
     if ((size_t)op.out.h * op.out.w < 64) return false;       // pooled 1x1 maps etc. stay on the CUDA-core kernel
-    if (op.res1 && op.res2) return false;
+    if (op.res1 && op.res2) return false;                     // the epilogue prefetches one residual source (no graph uses both)
+    if ((op.res1 || op.res2) && wt.cout % 4 != 0) return false;  // residual rows are prefetched in 16-byte pieces
+    if ((size_t)op.out.n * op.out.h * op.out.w >= ((size_t)1 << 31)) return false;   // 32-bit pixel indices in the kernel
     if (op.act == FCP_ACT_SIGMOID) return false;              // one activation form (leaky with slope 0 / 1 / s) in the compact epilogue                     // the epilogue prefetches one residual source (no graph uses both)
     return encode_fn() != nullptr;
 }
@@ -607,40 +624,47 @@ int launch_conv_tc(fcp_ctx* ctx, const ConvOp& op) {
     p.act = op.act; p.slope = op.slope;
     p.post_scale = op.post_scale; p.res2 = op.res2; p.res2_cs = op.res2_cs; p.res2_co = op.res2_co; p.res2_h = op.res2_h; p.res2_w = op.res2_w;
     p.post_scale2 = op.post_scale2; p.res3 = op.res3; p.res3_cs = op.res3_cs; p.res3_co = op.res3_co;
+    static const int exp_nolo = getenv("FCP_EXP_NOLO") ? atoi(getenv("FCP_EXP_NOLO")) : 0;
+    p.exp_nolo = exp_nolo;
+    auto do_launch = [&]() -> int {
+        if (BN == 128) return launch<128>(ctx, p);
+        if (BN == 64) return launch<64>(ctx, p);
+        return launch<32>(ctx, p);
+    };
 #ifdef FCP_EXP_TIMELINE
+    // clock64 stamps of CTA 0 for one launch of the shape FCP_TL_SHAPE="k,cin,cout" (default 3,256,256), K-blocks
+    // [FCP_TL_G0, FCP_TL_G0+FCP_TL_N) of launch number FCP_TL_SHOT of that shape
     static int shots = 0;
-    const bool shoot = getenv("FCP_TC_TIMELINE") && wt.k == 3 && wt.cin == 256 && wt.cout == 256 && shots < (getenv("FCP_TL_SHOT") ? atoi(getenv("FCP_TL_SHOT")) + 1 : 1) && p.N * p.Ho * p.Wo >= 65536;
+    auto envi = [](const char* n, int d) { const char* v = getenv(n); return v ? atoi(v) : d; };
+    int tk = 3, tcin = 256, tcout = 256;
+    if (const char* sh = getenv("FCP_TL_SHAPE")) sscanf(sh, "%d,%d,%d", &tk, &tcin, &tcout);
+    const int shot = envi("FCP_TL_SHOT", 0), g0 = envi("FCP_TL_G0", 100), gn = envi("FCP_TL_N", 24);
+    const bool shoot = getenv("FCP_TC_TIMELINE") && wt.k == tk && wt.cin == tcin && wt.cout == tcout && shots <= shot &&
+                       p.N * p.Ho * p.Wo >= 16384;
     long long* dbg = nullptr;
     if (shoot) { cudaMalloc(&dbg, 512 * 16 * 8); cudaMemset(dbg, 0, 512 * 16 * 8); p.dbg = dbg; ++shots; }
-    const bool print_it = shoot && shots == (getenv("FCP_TL_SHOT") ? atoi(getenv("FCP_TL_SHOT")) + 1 : 1);
-    int rc = BN == 128 ? launch<128, false>(ctx, p) : (BN == 64 ? launch<64, false>(ctx, p) : launch<32, false>(ctx, p));
-    if (shoot && !print_it) cudaFree(dbg);
+    const bool print_it = shoot && shots == shot + 1;
+    int rc = do_launch();
+    if (shoot && !print_it) { cudaStreamSynchronize(ctx->stream); cudaFree(dbg); }
     if (print_it) {
         cudaStreamSynchronize(ctx->stream);
         std::vector<long long> h(512 * 16);
         cudaMemcpy(h.data(), dbg, 512 * 16 * 8, cudaMemcpyDeviceToHost);
-        long long t0 = h[(getenv("FCP_TL_G0") ? atoi(getenv("FCP_TL_G0")) : 100) * 16 + 0];
-        fprintf(stderr, "[timeline] res1=%p res2=%p tiles=%d\n", (void*)p.res1, (void*)p.res2, p.num_tiles);
-        fprintf(stderr, "[timeline] g: prod_wait_empty prod_issued | mma_dempty mma_conv mma_issued | conv_full conv_done | drain_dfull drain_done\n");
-        for (int g = (getenv("FCP_TL_G0") ? atoi(getenv("FCP_TL_G0")) : 100); g < (getenv("FCP_TL_G0") ? atoi(getenv("FCP_TL_G0")) : 100) + 24; ++g) {
+        long long t0 = h[g0 * 16 + 0];
+        fprintf(stderr, "[timeline] k%d cin%d cout%d BN=%d res=%d kblocks/tile=%d tiles=%d\n", tk, tcin, tcout, BN, (int)(op.res1 || op.res2),
+                wt.k * wt.k * wt.cin / KB, p.num_tiles);
+        fprintf(stderr, "[timeline] g: prod_wait_empty prod_issued | mma_dempty mma_conv mma_issued | conv_full conv_done | drain_dfull drain_done | epi_done res_landed phase1_done om_done | tile_prologue_done\n");
+        for (int g = g0; g < g0 + gn && g < 512; ++g) {
             fprintf(stderr, "[timeline] %3d:", g);
-            for (int e = 0; e < 9; ++e) fprintf(stderr, " %7lld", h[g * 16 + e] ? h[g * 16 + e] - t0 : -1);
+            for (int e = 0; e < 14; ++e) fprintf(stderr, " %7lld", h[g * 16 + e] ? h[g * 16 + e] - t0 : -1);
             fprintf(stderr, "\n");
         }
         cudaFree(dbg);
     }
     return rc;
+#else
+    return do_launch();
 #endif
-    // residual-staging variant: tiles with a residual operand and a short K loop (their epilogue would otherwise wait on HBM)
-    const bool res = (op.res1 || op.res2) && wt.cout % 4 == 0 && getenv("FCP_TC_NO_RES") == nullptr;
-    if (res) {
-        if (BN == 128) return launch<128, true>(ctx, p);
-        if (BN == 64) return launch<64, true>(ctx, p);
-        return launch<32, true>(ctx, p);
-    }
-    if (BN == 128) return launch<128, false>(ctx, p);
-    if (BN == 64) return launch<64, false>(ctx, p);
-    return launch<32, false>(ctx, p);
 }
 
 }  // namespace fcp
