@@ -54,6 +54,8 @@ constexpr int NUM_THREADS = 32 * (14 + NUM_ISSUERS - 1);
 struct alignas(64) TcParams {
     CUtensorMap tmA[4];                        // input, one per (row parity, column parity); stride 1 uses [0]
     CUtensorMap tmBhi, tmBlo;                  // weights [cout_pad][K], K-major
+    CUtensorMap tmOut, tmRes;                  // output / residual tensor, box = one epilogue warp's 32 pixels x 32 channels
+    int out_tma, res_tma;                      // epilogue data paths: bulk tensor store / load usable for this launch
     int N, Ho, Wo, Cout, Cin, KH, KW, stride, pad;
     int tiles_x, tiles_y, tiles_n, num_tiles, bw_log2, BH;
     float* out; int out_cs, out_co;
@@ -97,6 +99,15 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// smem (128B-swizzled box) -> global tensor; completion tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src_smem, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk stores of this thread have finished READING shared memory (the slab may be overwritten)
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -132,6 +143,7 @@ __device__ __forceinline__ float lds_f1(uint32_t addr) {
 #endif
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+// generic-proxy writes to shared memory -> visible to the async proxy (TMA store source)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, one CTA
@@ -201,10 +213,15 @@ __device__ __forceinline__ float act_fn(float v, int act, float slope) {
     return v;
 }
 
-// One shared-memory slab per epilogue warp, S[32 pixels][BN/2 channels (+4 pad)], serves three purposes in turn: the
-// tile's residual operand (bottleneck shortcut / FPN top-down / RRDB skip) is prefetched into it with cp.async while the
-// K loop runs; the fused epilogue math then runs in place, pixel-per-thread (the TMEM lane layout); finally the slab is
-// read back transposed (channel-contiguous float4s) so that the output stores are full 128-byte lines.
+// Epilogue data path.  Every epilogue warp owns a shared-memory slab of CHUNKS x [32 pixels][32 channels] fp32 in the
+// 128B-swizzled layout TMA produces (16-byte piece c of pixel row r lives at r*128 + ((c ^ (r & 7)) << 4)):
+//   1. lane 0 bulk-loads the warp's residual sub-tile (bottleneck shortcut / RRDB skip) into it while the K loop runs,
+//   2. the fused epilogue math runs in place, pixel per thread (the TMEM lane layout; conflict-free thanks to the swizzle),
+//   3. lane 0 bulk-stores the slab to the output tensor (TMA clips rows / channels outside the tensor).
+// The warps never touch global memory with per-thread instructions on this path: measured, the per-thread version spent
+// ~2300 instructions per warp and tile on address arithmetic and was the bound of every layer with a short K loop.
+// Fallbacks (rolled loops): resized residual (FPN top-down add) via cp.async, per-thread stores when the output is
+// not 16-byte addressable (19-class logits) or carries the RRDB second residual.
 template <int BN> struct Cfg {
     static constexpr int B_TILE_BYTES = BN * KB * 4;
     static constexpr int STAGE_BYTES = A_TILE_BYTES + 2 * B_TILE_BYTES;   // fp32 A tile + w_hi + w_lo
@@ -213,13 +230,15 @@ template <int BN> struct Cfg {
     static constexpr int TMEM_A0 = 2 * BN;
     static constexpr int TMEM_COLS = 512;
     static_assert(TMEM_A0 + STAGES * 64 <= TMEM_COLS, "tensor memory budget");
-    static constexpr int HALF = BN / 2;                                   // channels owned by one epilogue warp
-    static constexpr int EPI_CW = HALF >= 32 ? 32 : 16;                   // channels per store chunk (32 -> full 128-byte lines)
-    static constexpr int S_LD = HALF + 4;                                 // floats per slab row (+4 pad: conflict-free float4s)
-    static constexpr int S_BYTES = 8 * 32 * S_LD * 4;                     // 8 epilogue warps x 32 pixels
-    static constexpr int PAR_BYTES = 8 * 2 * HALF * 4;                    // per warp: scale[HALF] | shift[HALF]
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + S_BYTES + PAR_BYTES;
+    static constexpr int EPI_WARPS = BN >= 64 ? 8 : 4;                    // BN=32: one warp per TMEM lane quarter
+    static constexpr int HALF = BN >= 64 ? BN / 2 : BN;                   // channels owned by one epilogue warp
+    static constexpr int CHUNKS = HALF / 32;                              // 32-channel (128-byte) chunks per warp
+    static constexpr int CHUNK_BYTES = 32 * 128;
+    static constexpr int S_BYTES = EPI_WARPS * CHUNKS * CHUNK_BYTES;
+    static constexpr int PAR_BYTES = EPI_WARPS * 2 * HALF * 4;            // per warp: scale[HALF] | shift[HALF]
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/ + S_BYTES + PAR_BYTES;
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+    static_assert(STAGE_BYTES % 1024 == 0, "the slab behind the stages must stay 1024-byte aligned (swizzle atoms)");
 };
 
 template <int BN>
@@ -227,15 +246,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     using C = Cfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+    uint8_t* slab_all = smem + C::STAGES * C::STAGE_BYTES;                                 // 1024-byte aligned: [EPI_WARPS][CHUNKS][32 rows][128 B]
+    float* par_all = reinterpret_cast<float*>(slab_all + C::S_BYTES);                      // [EPI_WARPS][2][HALF]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(slab_all + C::S_BYTES + C::PAR_BYTES);
     uint64_t* full = bars;                         // [STAGES]
     uint64_t* conv = bars + C::STAGES;             // [STAGES]
     uint64_t* empty = bars + 2 * C::STAGES;        // [STAGES]
     uint64_t* d_full = bars + 3 * C::STAGES;       // [2]  partial sum of one K-block is complete in TMEM buffer b
     uint64_t* d_empty = d_full + 2;                // [2]  buffer b has been drained to registers
-    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(d_empty + 2);
-    float* slab_all = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);   // [8 warps][32 rows][S_LD]
-    float* par_all = slab_all + C::S_BYTES / 4;                                            // [8 warps][2][HALF]
+    uint64_t* res_bar = d_empty + 2;               // [8]  residual sub-tile of epilogue warp w has landed
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(res_bar + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto stage_a = [&](int s) { return smem + s * C::STAGE_BYTES; };
@@ -244,7 +264,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&conv[s], 4); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&d_full[a], 1); mbar_init(&d_empty[a], 8); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&d_full[a], 1); mbar_init(&d_empty[a], C::EPI_WARPS); }
+        for (int a = 0; a < 8; ++a) mbar_init(&res_bar[a], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_base_smem, C::TMEM_COLS);
@@ -370,57 +391,78 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     } else if (warp < 14) {
         // ============================================================ accumulate + epilogue (warps 6..13, 256 threads)
         constexpr int HALF = C::HALF;                                         // columns owned by this warp
-        constexpr int CH = HALF >= 32 ? 32 : 16;                              // columns per tcgen05.ld
-        constexpr int NCH = HALF / CH;
-        constexpr int LD = C::S_LD;
+        constexpr int CHUNKS = C::CHUNKS;
+        const int ew = warp - 6;                                              // epilogue warp index
+        if (ew < C::EPI_WARPS) {
         const int quarter = warp & 3;                                         // TMEM lanes [32*quarter, 32*quarter+32)
-        const int half = (warp - 6) >> 2;
+        const int half = ew >> 2;
         const uint32_t lane_col = ((uint32_t)(quarter * 32) << 16) + half * HALF;
-        const uint32_t S = smem_u32(slab_all + (warp - 6) * 32 * LD);         // this warp's slab [32][LD] (shared-space address)
-        const uint32_t par = smem_u32(par_all + (warp - 6) * 2 * HALF);       // scale[HALF] | shift[HALF]
-        // store mapping: LPR lanes cover the CW contiguous channels of one pixel (CW=32: a full 128-byte line per pixel and
-        // store instruction), RPI pixels per instruction, NST instructions per 32-pixel chunk
-        constexpr int CW = C::EPI_CW, LPR = CW / 4, RPI = 32 / LPR, NST = 32 / RPI;
-        const int sub = lane % LPR, rbase = lane / LPR;
-        // residual prefetch mapping: RL lanes cover the HALF contiguous channels of one pixel, RR pixels per instruction
-        constexpr int RL = HALF / 4, RR = 32 / RL;
-        const int rcol = (lane % RL) * 4, rrow = lane / RL;
-        const float* __restrict__ rsrc = p.res1 ? p.res1 : p.res2;            // the graphs never use res1 and res2 together
-        const int r_cs = p.res1 ? p.res1_cs : p.res2_cs, r_co = p.res1 ? p.res1_co : p.res2_co;
-        const bool r_pre = p.res1 != nullptr, r_post = !r_pre && rsrc != nullptr;
-        const bool r_resize = !r_pre && p.res2_h != 0;                        // nearest resize of the added map (_layers.py:137-142)
-        const float rs_y = r_resize ? (float)p.res2_h / (float)p.Ho : 1.f, rs_x = r_resize ? (float)p.res2_w / (float)p.Wo : 1.f;
+        const uint32_t S = smem_u32(slab_all + ew * CHUNKS * C::CHUNK_BYTES); // this warp's slab: CHUNKS x [32 rows][128 B], swizzled
+        const uint32_t par = smem_u32(par_all + ew * 2 * HALF);               // scale[HALF] | shift[HALF]
+        uint64_t* const rbar = &res_bar[ew];
+        // swizzled address of 16-byte piece c (4 channels) of pixel row r in chunk q
+        auto slab_addr = [&](int q, int r, int c) -> uint32_t { return S + q * C::CHUNK_BYTES + r * 128 + ((c ^ (r & 7)) << 4); };
+        const bool has_res = p.res1 != nullptr || p.res2 != nullptr;          // the graphs never use res1 and res2 together
+        const bool r_pre = p.res1 != nullptr, r_post = !r_pre && has_res;
         const float neg_slope = p.act == FCP_ACT_NONE ? 1.f : (p.act == FCP_ACT_RELU ? 0.f : p.slope);
         const float post_scale = p.post_scale;
-        uint32_t g = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        // this warp's 32 pixels inside the tile's BH x BW box: rows [32*quarter, +32) in (w fastest) box order
+        const int sub_w = (quarter * 32) & (BW - 1), sub_h = (quarter * 32) >> p.bw_log2;
+        uint32_t g = 0, tile_par = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, tile_par ^= 1) {
             const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
             const int img = m_tile / tiles_per_img, rem = m_tile - img * tiles_per_img;
             const int ho0 = (rem / p.tiles_x) * p.BH, wo0 = (rem % p.tiles_x) * BW;
             const int n0 = n_tile * BN + half * HALF;                         // first channel of this warp
-            const int img_pix0 = img * p.Ho * p.Wo;
-            // ---- this warp's folded-BN scale/shift into shared memory (arrays are padded to cout_pad >= n0 + HALF)
-            for (int j = lane; j < HALF; j += 32) {
-                sts_f1(par + 4 * j, __ldg(p.scale + n0 + j));
-                sts_f1(par + 4 * (HALF + j), __ldg(p.shift + n0 + j));
-            }
-            // ---- residual sub-tile (32 pixels x HALF channels) streams into the slab while the K loop runs
-            if (rsrc && !(p.exp_nolo & 8)) {
-#pragma unroll 2
-                for (int it = 0; it < 32 / RR; ++it) {
-                    const int row = it * RR + rrow, prow = quarter * 32 + row;
-                    const int ho = ho0 + (prow >> p.bw_log2), wo = wo0 + (prow & (BW - 1));
-                    if (ho >= p.Ho || wo >= p.Wo || n0 + rcol + 3 >= p.Cout) continue;
-                    int rp = img_pix0 + ho * p.Wo + wo;
-                    if (r_resize) {
-                        const int hs = min((int)floorf(ho * rs_y), p.res2_h - 1), ws = min((int)floorf(wo * rs_x), p.res2_w - 1);
-                        rp = (img * p.res2_h + hs) * p.res2_w + ws;
-                    }
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(S + 4 * (row * LD + rcol)),
-                                 "l"(rsrc + (size_t)rp * r_cs + r_co + n0 + rcol) : "memory");
+            auto out_pixel = [&](int r) -> int {                              // output pixel of slab row r, -1 = outside the image
+                const int prow = quarter * 32 + r;
+                const int ho = ho0 + (prow >> p.bw_log2), wo = wo0 + (prow & (BW - 1));
+                return (ho < p.Ho && wo < p.Wo) ? (img * p.Ho + ho) * p.Wo + wo : -1;
+            };
+            // ---- this warp's folded-BN scale/shift into shared memory, asynchronously (arrays are padded to cout_pad >=
+            //      n0 + HALF): lanes [0, HALF/4) copy 16 bytes of scale, lanes [16, 16 + HALF/4) of shift
+            {
+                const int piece = lane & 15;
+                if (piece < HALF / 4) {
+                    const float* src = (lane < 16 ? p.scale : p.shift) + n0 + piece * 4;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(par + (lane < 16 ? 0 : 4 * HALF) + piece * 16), "l"(src) : "memory");
                 }
-                asm volatile("cp.async.commit_group;" ::: "memory");
             }
+            // ---- residual sub-tile (32 pixels x HALF channels) streams into the slab while the K loop runs.  The slab is
+            //      still being read by the previous tile's bulk store: the residual load is issued after the first K-block.
+            auto issue_residual = [&]() {
+                if (lane == 0) bulk_wait_read();                              // previous tile's store has released the slab
+                __syncwarp();
+                if (p.res_tma) {
+                    if (lane == 0) {
+                        mbar_expect_tx(rbar, CHUNKS * C::CHUNK_BYTES);
+#pragma unroll
+                        for (int q = 0; q < CHUNKS; ++q)
+                            tma_load_4d(slab_all + (ew * CHUNKS + q) * C::CHUNK_BYTES, &p.tmRes, rbar, n0 + q * 32, wo0 + sub_w, ho0 + sub_h, img);
+                    }
+                } else {
+                    // cp.async fallback (resized or unaligned residual): HALF/4 lanes cover one pixel, RR pixels per instruction
+                    constexpr int RL = HALF / 4, RR = 32 / RL;
+                    const int pc = lane % RL, rrow = lane / RL;               // 16-byte piece within the row
+                    const float* rsrc = p.res1 ? p.res1 : p.res2;
+                    const int r_cs = p.res1 ? p.res1_cs : p.res2_cs, r_co = p.res1 ? p.res1_co : p.res2_co;
+                    const bool r_resize = !r_pre && p.res2_h != 0;            // nearest resize of the added map (_layers.py:137-142)
+                    const float rs_y = (float)p.res2_h / (float)p.Ho, rs_x = (float)p.res2_w / (float)p.Wo;
+#pragma unroll 1
+                    for (int it = 0; it < 32 / RR; ++it) {
+                        const int row = it * RR + rrow, prow = quarter * 32 + row;
+                        const int ho = ho0 + (prow >> p.bw_log2), wo = wo0 + (prow & (BW - 1));
+                        if (ho >= p.Ho || wo >= p.Wo || n0 + pc * 4 + 3 >= p.Cout) continue;
+                        int rp = (img * p.Ho + ho) * p.Wo + wo;
+                        if (r_resize) {
+                            const int hs = min((int)floorf(ho * rs_y), p.res2_h - 1), ws = min((int)floorf(wo * rs_x), p.res2_w - 1);
+                            rp = (img * p.res2_h + hs) * p.res2_w + ws;
+                        }
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slab_addr(pc >> 3, row, pc & 7)),
+                                     "l"(rsrc + (size_t)rp * r_cs + r_co + n0 + pc * 4) : "memory");
+                    }
+                }
+            };
             float acc[HALF];
 #pragma unroll
             for (int j = 0; j < HALF; ++j) acc[j] = 0.f;
@@ -431,87 +473,104 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 if (warp == 6 && lane == 0) TL(g, 7);
                 tc_fence_after();
 #pragma unroll
-                for (int cb = 0; cb < NCH; ++cb) {
-                    float v[CH];
-                    tmem_ld<CH>(tmem_base + buf * BN + lane_col + cb * CH, v);
+                for (int cb = 0; cb < HALF / 32; ++cb) {
+                    float v[32];
+                    tmem_ld<32>(tmem_base + buf * BN + lane_col + cb * 32, v);
 #pragma unroll
-                    for (int j = 0; j < CH; ++j) acc[cb * CH + j] += v[j];     // round-to-nearest fp32 running sum
+                    for (int j = 0; j < 32; ++j) acc[cb * 32 + j] += v[j];     // round-to-nearest fp32 running sum
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&d_empty[buf]);
                 if (warp == 6 && lane == 0) TL(g, 8);
+                if (kb == 0 && has_res) issue_residual();
             }
-            // ---- fused epilogue, phase 1 (pixel per thread == TMEM lane, in place in the slab):
+            // ---- fused epilogue (pixel per thread == TMEM lane, in place in the slab):
             //      y = post_scale * act(acc * scale + shift [+ res1]) [+ res2]
-            if (rsrc) asm volatile("cp.async.wait_all;" ::: "memory");
+            asm volatile("cp.async.wait_all;" ::: "memory");                  // params (+ the cp.async residual)
+            if (has_res) {
+                if (p.res_tma) mbar_wait(rbar, tile_par);
+            } else if (lane == 0) {
+                bulk_wait_read();                                             // previous tile's store has released the slab
+            }
             __syncwarp();
             if (warp == 6 && lane == 0) TL(g - 1, 10);
-            if (!(p.exp_nolo & 4)) {
-                const uint32_t row = S + 4 * lane * LD;
+            {
+                // two 4-channel groups per step: their six shared-memory loads are in flight together (in-order issue,
+                // only two epilogue warps per scheduler to hide latency)
+                auto fuse = [&](const float a, const float sc, const float sh, const float rv) -> float {
+                    float x = a * sc + sh;
+                    if (r_pre) x += rv;
+                    x = fmaxf(x, x * neg_slope) * post_scale;                 // act in {none, relu, leaky}: 0 <= neg_slope <= 1
+                    if (r_post) x += rv;
+                    return x;
+                };
 #pragma unroll
-                for (int j = 0; j < HALF; j += 4) {
-                    const float4 sc = lds_f4(par + 4 * j);
-                    const float4 sh = lds_f4(par + 4 * (HALF + j));
-                    float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (rsrc) rv = lds_f4(row + 4 * j);
-                    float4 x;
-                    x.x = acc[j] * sc.x + sh.x; x.y = acc[j + 1] * sc.y + sh.y; x.z = acc[j + 2] * sc.z + sh.z; x.w = acc[j + 3] * sc.w + sh.w;
-                    if (r_pre) { x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w; }
-                    x.x = x.x > 0.f ? x.x : x.x * neg_slope; x.y = x.y > 0.f ? x.y : x.y * neg_slope;
-                    x.z = x.z > 0.f ? x.z : x.z * neg_slope; x.w = x.w > 0.f ? x.w : x.w * neg_slope;
-                    x.x *= post_scale; x.y *= post_scale; x.z *= post_scale; x.w *= post_scale;
-                    if (r_post) { x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w; }
-                    sts_f4(row + 4 * j, x);
+                for (int j = 0; j < HALF; j += 8) {
+                    const uint32_t a0 = slab_addr(j >> 5, lane, (j >> 2) & 7), a1 = slab_addr(j >> 5, lane, ((j >> 2) & 7) + 1);
+                    const float4 sc0 = lds_f4(par + 4 * j), sc1 = lds_f4(par + 4 * j + 16);
+                    const float4 sh0 = lds_f4(par + 4 * (HALF + j)), sh1 = lds_f4(par + 4 * (HALF + j) + 16);
+                    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+                    if (has_res) { r0 = lds_f4(a0); r1 = lds_f4(a1); }
+                    float4 x0, x1;
+                    x0.x = fuse(acc[j], sc0.x, sh0.x, r0.x); x0.y = fuse(acc[j + 1], sc0.y, sh0.y, r0.y);
+                    x0.z = fuse(acc[j + 2], sc0.z, sh0.z, r0.z); x0.w = fuse(acc[j + 3], sc0.w, sh0.w, r0.w);
+                    x1.x = fuse(acc[j + 4], sc1.x, sh1.x, r1.x); x1.y = fuse(acc[j + 5], sc1.y, sh1.y, r1.y);
+                    x1.z = fuse(acc[j + 6], sc1.z, sh1.z, r1.z); x1.w = fuse(acc[j + 7], sc1.w, sh1.w, r1.w);
+                    sts_f4(a0, x0);
+                    sts_f4(a1, x1);
                 }
             }
-            __syncwarp();
             if (warp == 6 && lane == 0) TL(g - 1, 11);
-            // ---- phase 2: read the slab back channel-contiguous; coalesced float4 stores (+ the RRDB second residual)
-            auto out_pixel = [&](int st) -> int {                             // output pixel of staged row rbase + RPI*st, -1 = outside
-                const int prow = quarter * 32 + rbase + RPI * st;
-                const int ho = ho0 + (prow >> p.bw_log2), wo = wo0 + (prow & (BW - 1));
-                return (ho < p.Ho && wo < p.Wo) ? img_pix0 + ho * p.Wo + wo : -1;
-            };
-            if (warp == 6 && lane == 0) TL(g - 1, 12);
-            // rolled loops on purpose: the epilogue runs once per tile, and straight-line code that does not fit the
-            // instruction caches is paced by instruction fetch (measured), not by the memory system
-            const bool has3 = p.res3 != nullptr;
+            if (p.out_tma) {
+                // ---- bulk tensor store of the slab (rows / channels outside the tensor are clipped by TMA)
+                fence_async_smem();
+                __syncwarp();
+                if (warp == 6 && lane == 0) TL(g - 1, 12);
+                if (lane == 0 && !(p.exp_nolo & 2)) {
+#pragma unroll
+                    for (int q = 0; q < CHUNKS; ++q)
+                        if (n0 + q * 32 < p.Cout) tma_store_4d(&p.tmOut, S + q * C::CHUNK_BYTES, n0 + q * 32, wo0 + sub_w, ho0 + sub_h, img);
+                    bulk_commit();
+                }
+            } else {
+                // ---- per-thread fallback: slab read back channel-contiguous (8 lanes cover the 128 bytes of one pixel and
+                //      chunk), + the RRDB second residual; scalar stores where Cout is not a multiple of 4 (19-class logits)
+                __syncwarp();
+                const int sub = lane & 7, rbase = lane >> 3;
+                const bool has3 = p.res3 != nullptr;
 #pragma unroll 1
-            for (int cc = 0; cc < HALF / CW; ++cc) {
-                const int cl = cc * CW + sub * 4, n = n0 + cl;                // channel within the slab / within the tensor
-                if (n + 3 < p.Cout) {
-                    float* const outp = p.out + p.out_co + n;
-                    const float* const r3p = p.res3 + p.res3_co + n;
-#pragma unroll 2
-                    for (int st = 0; st < NST; ++st) {
-                        const int m = out_pixel(st);
+                for (int q = 0; q < CHUNKS; ++q) {
+                    const int n = n0 + q * 32 + sub * 4;
+                    if (n >= p.Cout) continue;
+                    const bool vec = n + 3 < p.Cout && ((p.out_cs | p.out_co) & 3) == 0 && (!has3 || ((p.res3_cs | p.res3_co) & 3) == 0);
+#pragma unroll 1
+                    for (int st = 0; st < 8; ++st) {
+                        const int r = rbase + 4 * st, m = out_pixel(r);
                         if (m < 0) continue;
-                        float4 x = lds_f4(S + 4 * ((rbase + RPI * st) * LD + cl));
-                        if (has3) {
-                            const float4 r3 = __ldg(reinterpret_cast<const float4*>(r3p + (size_t)m * p.res3_cs));
-                            x.x = x.x * p.post_scale2 + r3.x; x.y = x.y * p.post_scale2 + r3.y;
-                            x.z = x.z * p.post_scale2 + r3.z; x.w = x.w * p.post_scale2 + r3.w;
-                        }
-                        if (!(p.exp_nolo & 2)) *reinterpret_cast<float4*>(outp + (size_t)m * p.out_cs) = x;
-                    }
-                } else if (n < p.Cout) {
-                    // ragged tail (Cout not a multiple of 4, e.g. the 19-class logits; never carries a residual): scalar stores
-#pragma unroll 1
-                    for (int st = 0; st < NST; ++st) {
-                        const int m = out_pixel(st);
-                        if (m < 0) continue;
-#pragma unroll 1
-                        for (int e = 0; e < 4 && n + e < p.Cout; ++e) {
-                            float x = lds_f1(S + 4 * ((rbase + RPI * st) * LD + cl + e));
-                            if (p.res3) x = x * p.post_scale2 + p.res3[(size_t)m * p.res3_cs + p.res3_co + n + e];
-                            p.out[(size_t)m * p.out_cs + p.out_co + n + e] = x;
+                        float4 x = lds_f4(slab_addr(q, r, sub));
+                        float* const op = p.out + (size_t)m * p.out_cs + p.out_co + n;
+                        const float* const r3 = has3 ? p.res3 + (size_t)m * p.res3_cs + p.res3_co + n : nullptr;
+                        if (vec) {
+                            if (has3) {
+                                const float4 t = __ldg(reinterpret_cast<const float4*>(r3));
+                                x.x = x.x * p.post_scale2 + t.x; x.y = x.y * p.post_scale2 + t.y;
+                                x.z = x.z * p.post_scale2 + t.z; x.w = x.w * p.post_scale2 + t.w;
+                            }
+                            *reinterpret_cast<float4*>(op) = x;
+                        } else {
+                            const float xe[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (n + e < p.Cout) op[e] = has3 ? xe[e] * p.post_scale2 + r3[e] : xe[e];
                         }
                     }
                 }
+                __syncwarp();                                                 // slab + params are rewritten by the next tile
             }
-            __syncwarp();                                                     // slab + params are rewritten by the next tile
             if (warp == 6 && lane == 0) TL(g - 1, 9);                        // epilogue of this tile finished
+        }
+        if (lane == 0) bulk_wait_all();                                       // global writes of the last tile complete before exit
         }
     }
     tc_fence_before();
@@ -618,6 +677,25 @@ int launch_conv_tc(fcp_ctx* ctx, const ConvOp& op) {
     cuuint32_t bbox[2] = {KB, (cuuint32_t)BN};
     if (!make_map(&p.tmBhi, wt.w_hi, 2, bdims, bstr, bbox) || !make_map(&p.tmBlo, wt.w_lo, 2, bdims, bstr, bbox))
         return fail(ctx, FCP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the weights");
+    // ---- epilogue tensor maps: one box = the 32 pixels x 32 channels of one epilogue warp and chunk
+    {
+        const int bws = BW < 32 ? BW : 32, bhs = 32 / bws;
+        auto tensor_ok = [](const float* base, int cs) { return cs % 4 == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0; };
+        auto epi_map = [&](CUtensorMap* map, const float* base, int cs) {
+            cuuint64_t dims[4] = {(cuuint64_t)wt.cout, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)p.N};
+            cuuint64_t strides[3] = {(cuuint64_t)cs * 4, (cuuint64_t)p.Wo * cs * 4, (cuuint64_t)p.Ho * p.Wo * cs * 4};
+            cuuint32_t box[4] = {32, (cuuint32_t)bws, (cuuint32_t)bhs, 1};
+            return make_map(map, const_cast<float*>(base), 4, dims, strides, box);
+        };
+        p.out_tma = !op.res3 && tensor_ok(op.out.p + op.out.co, op.out.cs) && getenv("FCP_TC_NO_TMA_EPI") == nullptr;
+        if (p.out_tma && !epi_map(&p.tmOut, op.out.p + op.out.co, op.out.cs))
+            return fail(ctx, FCP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the output tensor");
+        const float* rsrc = op.res1 ? op.res1 : op.res2;
+        const int r_cs = op.res1 ? op.res1_cs : op.res2_cs, r_co = op.res1 ? op.res1_co : op.res2_co;
+        p.res_tma = rsrc && !(op.res2 && op.res2_h) && tensor_ok(rsrc + r_co, r_cs) && getenv("FCP_TC_NO_TMA_EPI") == nullptr;
+        if (p.res_tma && !epi_map(&p.tmRes, rsrc + r_co, r_cs))
+            return fail(ctx, FCP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the residual tensor");
+    }
     p.out = op.out.p; p.out_cs = op.out.cs; p.out_co = op.out.co;
     p.scale = wt.scale; p.shift = wt.shift;
     p.res1 = op.res1; p.res1_cs = op.res1_cs; p.res1_co = op.res1_co;
