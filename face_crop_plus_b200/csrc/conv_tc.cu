@@ -54,7 +54,7 @@ constexpr int NUM_THREADS = 32 * (14 + NUM_ISSUERS - 1);
 struct alignas(64) TcParams {
     CUtensorMap tmA[4];                        // input, one per (row parity, column parity); stride 1 uses [0]
     CUtensorMap tmBhi, tmBlo;                  // weights [cout_pad][K], K-major
-    CUtensorMap tmOut, tmRes;                  // output / residual tensor, box = one epilogue warp's 32 pixels x 32 channels
+    CUtensorMap tmOut, tmRes;                  // output / residual tensor, box = the tile's 128 pixels x 32 channels
     int out_tma, res_tma;                      // epilogue data paths: bulk tensor store / load usable for this launch
     int N, Ho, Wo, Cout, Cin, KH, KW, stride, pad;
     int tiles_x, tiles_y, tiles_n, num_tiles, bw_log2, BH;
@@ -213,11 +213,14 @@ __device__ __forceinline__ float act_fn(float v, int act, float slope) {
     return v;
 }
 
-// Epilogue data path.  Every epilogue warp owns a shared-memory slab of CHUNKS x [32 pixels][32 channels] fp32 in the
-// 128B-swizzled layout TMA produces (16-byte piece c of pixel row r lives at r*128 + ((c ^ (r & 7)) << 4)):
-//   1. lane 0 bulk-loads the warp's residual sub-tile (bottleneck shortcut / RRDB skip) into it while the K loop runs,
+// Epilogue data path.  The 4 epilogue warps that share a channel half (one warp per TMEM lane quarter = 32 pixels) own a
+// shared-memory slab of CHUNKS x [128 pixels][32 channels] fp32 in the 128B-swizzled layout TMA produces (16-byte piece c
+// of pixel row r lives at r*128 + ((c ^ (r & 7)) << 4)); chunk q of the group is driven by lane 0 of its quarter-q warp:
+//   1. it bulk-loads the tile's residual chunk (bottleneck shortcut / RRDB skip) into the slab while the K loop runs,
 //   2. the fused epilogue math runs in place, pixel per thread (the TMEM lane layout; conflict-free thanks to the swizzle),
-//   3. lane 0 bulk-stores the slab to the output tensor (TMA clips rows / channels outside the tensor).
+//   3. it bulk-stores the chunk to the output tensor (TMA clips rows / channels outside the tensor).
+// One TMA operation costs the issuing thread 75-150 cycles of TMA-unit time whatever its size (measured), hence whole
+// 16 KiB chunks per operation and a 128-thread named barrier per group instead of one operation per warp.
 // The warps never touch global memory with per-thread instructions on this path: measured, the per-thread version spent
 // ~2300 instructions per warp and tile on address arithmetic and was the bound of every layer with a short K loop.
 // Fallbacks (rolled loops): resized residual (FPN top-down add) via cp.async, per-thread stores when the output is
@@ -232,10 +235,11 @@ template <int BN> struct Cfg {
     static_assert(TMEM_A0 + STAGES * 64 <= TMEM_COLS, "tensor memory budget");
     static constexpr int EPI_WARPS = BN >= 64 ? 8 : 4;                    // BN=32: one warp per TMEM lane quarter
     static constexpr int HALF = BN >= 64 ? BN / 2 : BN;                   // channels owned by one epilogue warp
-    static constexpr int CHUNKS = HALF / 32;                              // 32-channel (128-byte) chunks per warp
-    static constexpr int CHUNK_BYTES = 32 * 128;
-    static constexpr int S_BYTES = EPI_WARPS * CHUNKS * CHUNK_BYTES;
-    static constexpr int PAR_BYTES = EPI_WARPS * 2 * HALF * 4;            // per warp: scale[HALF] | shift[HALF]
+    static constexpr int GROUPS = EPI_WARPS / 4;                          // 4 warps (all 128 pixels) share HALF channels
+    static constexpr int CHUNKS = HALF / 32;                              // 32-channel (128-byte) chunks per group
+    static constexpr int CHUNK_BYTES = TILE_M * 128;                      // one chunk = the tile's 128 pixels x 32 channels
+    static constexpr int S_BYTES = GROUPS * CHUNKS * CHUNK_BYTES;
+    static constexpr int PAR_BYTES = GROUPS * 2 * HALF * 4;               // per group: scale[HALF] | shift[HALF]
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/ + S_BYTES + PAR_BYTES;
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
     static_assert(STAGE_BYTES % 1024 == 0, "the slab behind the stages must stay 1024-byte aligned (swizzle atoms)");
@@ -246,15 +250,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     using C = Cfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* slab_all = smem + C::STAGES * C::STAGE_BYTES;                                 // 1024-byte aligned: [EPI_WARPS][CHUNKS][32 rows][128 B]
-    float* par_all = reinterpret_cast<float*>(slab_all + C::S_BYTES);                      // [EPI_WARPS][2][HALF]
+    uint8_t* slab_all = smem + C::STAGES * C::STAGE_BYTES;                                 // 1024-byte aligned: [GROUPS][CHUNKS][128 rows][128 B]
+    float* par_all = reinterpret_cast<float*>(slab_all + C::S_BYTES);                      // [GROUPS][2][HALF]
     uint64_t* bars = reinterpret_cast<uint64_t*>(slab_all + C::S_BYTES + C::PAR_BYTES);
     uint64_t* full = bars;                         // [STAGES]
     uint64_t* conv = bars + C::STAGES;             // [STAGES]
     uint64_t* empty = bars + 2 * C::STAGES;        // [STAGES]
     uint64_t* d_full = bars + 3 * C::STAGES;       // [2]  partial sum of one K-block is complete in TMEM buffer b
     uint64_t* d_empty = d_full + 2;                // [2]  buffer b has been drained to registers
-    uint64_t* res_bar = d_empty + 2;               // [8]  residual sub-tile of epilogue warp w has landed
+    uint64_t* res_bar = d_empty + 2;               // [8]  (first GROUPS used) residual chunks of the group's tile have landed
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(res_bar + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -265,7 +269,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&conv[s], 4); mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&d_full[a], 1); mbar_init(&d_empty[a], C::EPI_WARPS); }
-        for (int a = 0; a < 8; ++a) mbar_init(&res_bar[a], 1);
+        for (int a = 0; a < 8; ++a) mbar_init(&res_bar[a], C::CHUNKS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_base_smem, C::TMEM_COLS);
@@ -397,48 +401,52 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         const int quarter = warp & 3;                                         // TMEM lanes [32*quarter, 32*quarter+32)
         const int half = ew >> 2;
         const uint32_t lane_col = ((uint32_t)(quarter * 32) << 16) + half * HALF;
-        const uint32_t S = smem_u32(slab_all + ew * CHUNKS * C::CHUNK_BYTES); // this warp's slab: CHUNKS x [32 rows][128 B], swizzled
-        const uint32_t par = smem_u32(par_all + ew * 2 * HALF);               // scale[HALF] | shift[HALF]
-        uint64_t* const rbar = &res_bar[ew];
-        // swizzled address of 16-byte piece c (4 channels) of pixel row r in chunk q
-        auto slab_addr = [&](int q, int r, int c) -> uint32_t { return S + q * C::CHUNK_BYTES + r * 128 + ((c ^ (r & 7)) << 4); };
+        const uint32_t S = smem_u32(slab_all + half * CHUNKS * C::CHUNK_BYTES);   // the group's slab: CHUNKS x [128 rows][128 B], swizzled
+        const uint32_t par = smem_u32(par_all + half * 2 * HALF);             // the group's scale[HALF] | shift[HALF]
+        uint64_t* const rbar = &res_bar[half];
+        // swizzled address of 16-byte piece c (4 channels) of this warp's pixel row r (0..31) in chunk q
+        auto slab_addr = [&](int q, int r, int c) -> uint32_t {
+            return S + q * C::CHUNK_BYTES + (quarter * 32 + r) * 128 + ((c ^ (r & 7)) << 4);
+        };
+        auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory"); };   // the 4 warps of this half
         const bool has_res = p.res1 != nullptr || p.res2 != nullptr;          // the graphs never use res1 and res2 together
         const bool r_pre = p.res1 != nullptr, r_post = !r_pre && has_res;
         const float neg_slope = p.act == FCP_ACT_NONE ? 1.f : (p.act == FCP_ACT_RELU ? 0.f : p.slope);
         const float post_scale = p.post_scale;
-        // this warp's 32 pixels inside the tile's BH x BW box: rows [32*quarter, +32) in (w fastest) box order
-        const int sub_w = (quarter * 32) & (BW - 1), sub_h = (quarter * 32) >> p.bw_log2;
+        const bool dma = lane == 0 && quarter < CHUNKS;                       // this thread drives the TMA traffic of chunk `quarter`
         uint32_t g = 0, tile_par = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, tile_par ^= 1) {
             const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
             const int img = m_tile / tiles_per_img, rem = m_tile - img * tiles_per_img;
             const int ho0 = (rem / p.tiles_x) * p.BH, wo0 = (rem % p.tiles_x) * BW;
-            const int n0 = n_tile * BN + half * HALF;                         // first channel of this warp
-            auto out_pixel = [&](int r) -> int {                              // output pixel of slab row r, -1 = outside the image
+            const int n0 = n_tile * BN + half * HALF;                         // first channel of this group
+            auto out_pixel = [&](int r) -> int {                              // output pixel of this warp's row r, -1 = outside the image
                 const int prow = quarter * 32 + r;
                 const int ho = ho0 + (prow >> p.bw_log2), wo = wo0 + (prow & (BW - 1));
                 return (ho < p.Ho && wo < p.Wo) ? (img * p.Ho + ho) * p.Wo + wo : -1;
             };
-            // ---- this warp's folded-BN scale/shift into shared memory, asynchronously (arrays are padded to cout_pad >=
-            //      n0 + HALF): lanes [0, HALF/4) copy 16 bytes of scale, lanes [16, 16 + HALF/4) of shift
-            {
+            // ---- the group's folded-BN scale/shift into shared memory, asynchronously, by the quarter-3 warp (arrays are
+            //      padded to cout_pad >= n0 + HALF): lanes [0, HALF/4) copy 16 bytes of scale, lanes [16, 16 + HALF/4) of shift.
+            //      Safe to overwrite: every warp of the group has passed the pre-store barrier of the previous tile.
+            if (quarter == 3) {
                 const int piece = lane & 15;
                 if (piece < HALF / 4) {
                     const float* src = (lane < 16 ? p.scale : p.shift) + n0 + piece * 4;
                     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(par + (lane < 16 ? 0 : 4 * HALF) + piece * 16), "l"(src) : "memory");
                 }
             }
-            // ---- residual sub-tile (32 pixels x HALF channels) streams into the slab while the K loop runs.  The slab is
-            //      still being read by the previous tile's bulk store: the residual load is issued after the first K-block.
-            auto issue_residual = [&]() {
-                if (lane == 0) bulk_wait_read();                              // previous tile's store has released the slab
-                __syncwarp();
+            // ---- after the first K-block: the previous tile's bulk stores have released the slab (waited for by the threads
+            //      that issued them), the params have landed; one group barrier publishes both, then the residual chunks
+            //      (128 pixels x 32 channels each) stream into the slab while the K loop runs.
+            auto after_first_kblock = [&]() {
+                if (dma) bulk_wait_read();
+                if (quarter == 3) asm volatile("cp.async.wait_all;" ::: "memory");
+                group_sync();
+                if (!has_res) return;
                 if (p.res_tma) {
-                    if (lane == 0) {
-                        mbar_expect_tx(rbar, CHUNKS * C::CHUNK_BYTES);
-#pragma unroll
-                        for (int q = 0; q < CHUNKS; ++q)
-                            tma_load_4d(slab_all + (ew * CHUNKS + q) * C::CHUNK_BYTES, &p.tmRes, rbar, n0 + q * 32, wo0 + sub_w, ho0 + sub_h, img);
+                    if (dma) {
+                        mbar_expect_tx(rbar, C::CHUNK_BYTES);
+                        tma_load_4d(slab_all + (half * CHUNKS + quarter) * C::CHUNK_BYTES, &p.tmRes, rbar, n0 + quarter * 32, wo0, ho0, img);
                     }
                 } else {
                     // cp.async fallback (resized or unaligned residual): HALF/4 lanes cover one pixel, RR pixels per instruction
@@ -483,15 +491,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&d_empty[buf]);
                 if (warp == 6 && lane == 0) TL(g, 8);
-                if (kb == 0 && has_res) issue_residual();
+                if (kb == 0) after_first_kblock();
             }
             // ---- fused epilogue (pixel per thread == TMEM lane, in place in the slab):
             //      y = post_scale * act(acc * scale + shift [+ res1]) [+ res2]
-            asm volatile("cp.async.wait_all;" ::: "memory");                  // params (+ the cp.async residual)
             if (has_res) {
                 if (p.res_tma) mbar_wait(rbar, tile_par);
-            } else if (lane == 0) {
-                bulk_wait_read();                                             // previous tile's store has released the slab
+                else asm volatile("cp.async.wait_all;" ::: "memory");         // this warp's own rows
             }
             __syncwarp();
             if (warp == 6 && lane == 0) TL(g - 1, 10);
@@ -525,18 +531,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             if (p.out_tma) {
                 // ---- bulk tensor store of the slab (rows / channels outside the tensor are clipped by TMA)
                 fence_async_smem();
-                __syncwarp();
+                group_sync();                                                 // all 128 pixel rows of the group's chunks are final
                 if (warp == 6 && lane == 0) TL(g - 1, 12);
-                if (lane == 0 && !(p.exp_nolo & 2)) {
-#pragma unroll
-                    for (int q = 0; q < CHUNKS; ++q)
-                        if (n0 + q * 32 < p.Cout) tma_store_4d(&p.tmOut, S + q * C::CHUNK_BYTES, n0 + q * 32, wo0 + sub_w, ho0 + sub_h, img);
+                if (dma && !(p.exp_nolo & 2)) {
+                    if (n0 + quarter * 32 < p.Cout) tma_store_4d(&p.tmOut, S + quarter * C::CHUNK_BYTES, n0 + quarter * 32, wo0, ho0, img);
                     bulk_commit();
                 }
             } else {
                 // ---- per-thread fallback: slab read back channel-contiguous (8 lanes cover the 128 bytes of one pixel and
                 //      chunk), + the RRDB second residual; scalar stores where Cout is not a multiple of 4 (19-class logits)
-                __syncwarp();
+                __syncwarp();                                                 // (only this warp's own rows are read back)
                 const int sub = lane & 7, rbase = lane >> 3;
                 const bool has3 = p.res3 != nullptr;
 #pragma unroll 1
@@ -566,11 +570,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                         }
                     }
                 }
-                __syncwarp();                                                 // slab + params are rewritten by the next tile
+                group_sync();                                                 // slab + params are rewritten by the next tile
             }
             if (warp == 6 && lane == 0) TL(g - 1, 9);                        // epilogue of this tile finished
         }
-        if (lane == 0) bulk_wait_all();                                       // global writes of the last tile complete before exit
+        if (dma) bulk_wait_all();                                       // global writes of the last tile complete before exit
         }
     }
     tc_fence_before();
@@ -677,9 +681,9 @@ int launch_conv_tc(fcp_ctx* ctx, const ConvOp& op) {
     cuuint32_t bbox[2] = {KB, (cuuint32_t)BN};
     if (!make_map(&p.tmBhi, wt.w_hi, 2, bdims, bstr, bbox) || !make_map(&p.tmBlo, wt.w_lo, 2, bdims, bstr, bbox))
         return fail(ctx, FCP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the weights");
-    // ---- epilogue tensor maps: one box = the 32 pixels x 32 channels of one epilogue warp and chunk
+    // ---- epilogue tensor maps: one box = the tile's 128 pixels x 32 channels (one chunk of an epilogue group)
     {
-        const int bws = BW < 32 ? BW : 32, bhs = 32 / bws;
+        const int bws = BW, bhs = BH;
         auto tensor_ok = [](const float* base, int cs) { return cs % 4 == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0; };
         auto epi_map = [&](CUtensorMap* map, const float* base, int cs) {
             cuuint64_t dims[4] = {(cuuint64_t)wt.cout, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)p.N};
