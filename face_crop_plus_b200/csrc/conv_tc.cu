@@ -25,9 +25,9 @@
 //   the block's partial sum is drained to fp32 registers and added there with round-to-nearest.
 //
 // CTA = 15 warps, persistent over output tiles (128 pixels x BN channels):
-//   warp 0      TMA producer          full[s]  <- TMA bytes          (waits empty[s])
-//   warps 2-5   hi/lo converters      conv[s]  <- 4 arrivals (1/warp) (wait full[s])
-//   warps 1,14  MMA issuers (1 lane each, alternating K-blocks)  empty[s], d_full[b] <- tcgen05.commit (wait conv[s], d_empty[b])
+//   warp 0      TMA producer          full_a[l] <- A bytes (waits a_free[l]);  full_b[s] <- weight bytes (waits empty[s])
+//   warps 2-5   hi/lo converters      a_free[l], conv[s] <- 4 arrivals (1/warp) (wait full_a[l], then empty[s] for the TMEM slot)
+//   warps 1,14  MMA issuers (1 lane each, alternating K-blocks)  empty[s], d_full[b] <- tcgen05.commit (wait conv[s], full_b[s], d_empty[b])
 //   warps 6-13  accumulate+epilogue   d_empty[b] <- 8 arrivals (1/warp) (wait d_full[b]); per K-block TMEM -> regs (+=),
 //               after the last K-block: fused epilogue -> HBM.  Warp w owns TMEM lanes 32*(w%4).. and half of the columns.
 // Two TMEM partial-sum buffers let the drain of K-block i overlap the MMAs of K-block i+1.
@@ -187,6 +187,15 @@ template <> __device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, float* v
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// issue only (no wait): the caller overlaps the load with arithmetic on the previous piece and then calls tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 template <> __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float* v) {
     uint32_t r[16];
     asm volatile(
@@ -227,8 +236,13 @@ __device__ __forceinline__ float act_fn(float v, int act, float slope) {
 // not 16-byte addressable (19-class logits) or carries the RRDB second residual.
 template <int BN> struct Cfg {
     static constexpr int B_TILE_BYTES = BN * KB * 4;
-    static constexpr int STAGE_BYTES = A_TILE_BYTES + 2 * B_TILE_BYTES;   // fp32 A tile + w_hi + w_lo
-    static constexpr int STAGES = BN >= 128 ? 3 : (BN == 64 ? 5 : 7);
+    static constexpr int B_SLOT_BYTES = 2 * B_TILE_BYTES;                 // w_hi + w_lo of one K-block
+    // The K loop is bound by the latency of one trip round the pipeline (TMA issue + landing + convert + MMA issue +
+    // retire ~ 3300 cycles, measured) divided by its depth, not by any bandwidth.  The fp32 A tile only lives from its
+    // landing to its conversion, so it gets its own short ring (LANDINGS); a pipeline STAGE is a weight slot in shared
+    // memory plus an (a_hi | a_lo) slot in tensor memory, both held until the K-block's MMAs retire.
+    static constexpr int STAGES = BN >= 128 ? 4 : (BN == 64 ? 6 : 7);
+    static constexpr int LANDINGS = BN >= 128 ? 2 : 3;
     // tensor memory: [0, 2*BN) two partial-sum buffers; then STAGES x (a_hi 32 cols | a_lo 32 cols)
     static constexpr int TMEM_A0 = 2 * BN;
     static constexpr int TMEM_COLS = 512;
@@ -240,9 +254,10 @@ template <int BN> struct Cfg {
     static constexpr int CHUNK_BYTES = TILE_M * 128;                      // one chunk = the tile's 128 pixels x 32 channels
     static constexpr int S_BYTES = GROUPS * CHUNKS * CHUNK_BYTES;
     static constexpr int PAR_BYTES = GROUPS * 2 * HALF * 4;               // per group: scale[HALF] | shift[HALF]
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/ + S_BYTES + PAR_BYTES;
+    static constexpr int PIPE_BYTES = STAGES * B_SLOT_BYTES + LANDINGS * A_TILE_BYTES;
+    static constexpr int SMEM_BYTES = PIPE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/ + S_BYTES + PAR_BYTES;
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
-    static_assert(STAGE_BYTES % 1024 == 0, "the slab behind the stages must stay 1024-byte aligned (swizzle atoms)");
+    static_assert(B_SLOT_BYTES % 1024 == 0 && B_TILE_BYTES % 1024 == 0, "operand tiles must stay 1024-byte aligned (swizzle atoms)");
 };
 
 template <int BN>
@@ -250,26 +265,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     using C = Cfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* slab_all = smem + C::STAGES * C::STAGE_BYTES;                                 // 1024-byte aligned: [GROUPS][CHUNKS][128 rows][128 B]
+    // [STAGES x (w_hi | w_lo)] [LANDINGS x fp32 A tile] [slab: GROUPS x CHUNKS x 128 rows x 128 B] [params] [barriers]
+    uint8_t* slab_all = smem + C::PIPE_BYTES;                                              // 1024-byte aligned
     float* par_all = reinterpret_cast<float*>(slab_all + C::S_BYTES);                      // [GROUPS][2][HALF]
     uint64_t* bars = reinterpret_cast<uint64_t*>(slab_all + C::S_BYTES + C::PAR_BYTES);
-    uint64_t* full = bars;                         // [STAGES]
-    uint64_t* conv = bars + C::STAGES;             // [STAGES]
-    uint64_t* empty = bars + 2 * C::STAGES;        // [STAGES]
-    uint64_t* d_full = bars + 3 * C::STAGES;       // [2]  partial sum of one K-block is complete in TMEM buffer b
+    uint64_t* full_b = bars;                       // [STAGES]   weights of the K-block have landed
+    uint64_t* conv = bars + C::STAGES;             // [STAGES]   a_hi | a_lo of the K-block are in the stage's TMEM slot
+    uint64_t* empty = bars + 2 * C::STAGES;        // [STAGES]   the K-block's MMAs have retired: weight slot + TMEM slot reusable
+    uint64_t* full_a = bars + 3 * C::STAGES;       // [LANDINGS] fp32 A tile has landed
+    uint64_t* a_free = full_a + C::LANDINGS;       // [LANDINGS] the converters have read the landing buffer
+    uint64_t* d_full = a_free + C::LANDINGS;       // [2]  partial sum of one K-block is complete in TMEM buffer b
     uint64_t* d_empty = d_full + 2;                // [2]  buffer b has been drained to registers
-    uint64_t* res_bar = d_empty + 2;               // [8]  (first GROUPS used) residual chunks of the group's tile have landed
-    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(res_bar + 8);
+    uint64_t* res_bar = d_empty + 2;               // [2]  (first GROUPS used) residual chunks of the group's tile have landed
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(res_bar + 2);
+    static_assert((3 * C::STAGES + 2 * C::LANDINGS + 6) * 8 + 4 <= 512, "barrier area");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    auto stage_a = [&](int s) { return smem + s * C::STAGE_BYTES; };
-    auto stage_b_hi = [&](int s) { return smem + s * C::STAGE_BYTES + A_TILE_BYTES; };
-    auto stage_b_lo = [&](int s) { return smem + s * C::STAGE_BYTES + A_TILE_BYTES + C::B_TILE_BYTES; };
+    auto stage_b_hi = [&](int s) { return smem + s * C::B_SLOT_BYTES; };
+    auto stage_b_lo = [&](int s) { return smem + s * C::B_SLOT_BYTES + C::B_TILE_BYTES; };
+    auto landing = [&](int l) { return smem + C::STAGES * C::B_SLOT_BYTES + l * A_TILE_BYTES; };
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&conv[s], 4); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&d_full[a], 1); mbar_init(&d_empty[a], C::EPI_WARPS); }
-        for (int a = 0; a < 8; ++a) mbar_init(&res_bar[a], C::CHUNKS);
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_b[s], 1); mbar_init(&conv[s], 4); mbar_init(&empty[s], 1); }
+        for (int l = 0; l < C::LANDINGS; ++l) { mbar_init(&full_a[l], 1); mbar_init(&a_free[l], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&d_full[a], 1); mbar_init(&d_empty[a], C::EPI_WARPS); mbar_init(&res_bar[a], C::CHUNKS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_base_smem, C::TMEM_COLS);
@@ -286,7 +305,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     if (warp == 0) {
         // ================================================================================== TMA producer
         if (lane == 0) {
-            int stage = 0; uint32_t phase = 0; uint32_t gp = 0; (void)gp;
+            int stage = 0, land = 0; uint32_t phase = 0, lphase = 0; uint32_t gp = 0; (void)gp;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
                 const int img = m_tile / tiles_per_img, rem = m_tile - img * tiles_per_img;
@@ -301,15 +320,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                         dx = (dx - px) >> 1;
                     }
                     const int c0 = cc * KB, kcol = tap * p.Cin + c0;
-                    mbar_wait<true>(&empty[stage], phase ^ 1);
+                    // the activation tile first (it has the longer way to go: landing -> converters -> tensor memory)
+                    mbar_wait<true>(&a_free[land], lphase ^ 1);
                     TL(gp, 0);
-                    mbar_expect_tx(&full[stage], A_TILE_BYTES + ((p.exp_nolo & 1) ? 1 : 2) * C::B_TILE_BYTES);
-                    tma_load_4d(stage_a(stage), &p.tmA[map], &full[stage], c0, wo0 + dx, ho0 + dy, img);
-                    tma_load_2d(stage_b_hi(stage), &p.tmBhi, &full[stage], kcol, n_tile * BN);
-                    if (!(p.exp_nolo & 1)) tma_load_2d(stage_b_lo(stage), &p.tmBlo, &full[stage], kcol, n_tile * BN);
+                    mbar_expect_tx(&full_a[land], A_TILE_BYTES);
+                    tma_load_4d(landing(land), &p.tmA[map], &full_a[land], c0, wo0 + dx, ho0 + dy, img);
+                    mbar_wait<true>(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full_b[stage], ((p.exp_nolo & 1) ? 1 : 2) * C::B_TILE_BYTES);
+                    tma_load_2d(stage_b_hi(stage), &p.tmBhi, &full_b[stage], kcol, n_tile * BN);
+                    if (!(p.exp_nolo & 1)) tma_load_2d(stage_b_lo(stage), &p.tmBlo, &full_b[stage], kcol, n_tile * BN);
                     if (++cc == cchunks) { cc = 0; ++tap; if (++sx == p.KW) { sx = 0; ++r; } }
                     TL(gp, 1); ++gp;
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    if (++land == C::LANDINGS) { land = 0; lphase ^= 1; }
                 }
             }
         }
@@ -328,12 +351,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 for (int kb = 0; kb < kblocks; ++kb, ++g) {
                     if (g % NUM_ISSUERS == me) {
                         const uint32_t buf = g & 1;
-                        if (p.exp_nolo & 16) mbar_wait<true>(&d_empty[buf], ((g >> 1) & 1) ^ 1);
-                        else mbar_wait(&d_empty[buf], ((g >> 1) & 1) ^ 1);    // partial-sum buffer drained
-                        TL(g, 2);
-                        if (p.exp_nolo & 16) mbar_wait<true>(&conv[stage], phase);
-                        else mbar_wait(&conv[stage], phase);                  // operands (hi/lo) ready
+                        // operands first (normally long complete), the partial-sum buffer last: its release by the drain
+                        // warps is the critical dependency of this thread's K-block chain
+                        mbar_wait(&full_b[stage], phase);                     // weights landed
+                        mbar_wait(&conv[stage], phase);                       // a_hi | a_lo converted into the stage's TMEM slot
                         TL(g, 3);
+                        mbar_wait(&d_empty[buf], ((g >> 1) & 1) ^ 1);         // partial-sum buffer drained
+                        TL(g, 2);
                         tc_fence_after();
                         const uint32_t d_tmem = tmem_base + buf * BN;
                         const uint32_t a_hi = tmem_base + C::TMEM_A0 + stage * 64, a_lo = a_hi + 32;   // A operand: tensor memory
@@ -361,12 +385,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-        int stage = 0; uint32_t phase = 0; uint32_t gc = 0; (void)gc;
+        int stage = 0, land = 0; uint32_t phase = 0, lphase = 0; uint32_t gc = 0; (void)gc;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             for (int kb = 0; kb < kblocks; ++kb) {
-                mbar_wait<true>(&full[stage], phase);
+                mbar_wait<true>(&full_a[land], lphase);
                 if (warp == 2 && lane == 0) TL(gc, 5);
-                const uint32_t src = smem_u32(stage_a(stage)) + row * 128;
+                const uint32_t src = smem_u32(landing(land)) + row * 128;
                 uint4 v[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) v[c] = lds128(src + (uint32_t)((c ^ (row & 7)) << 4));   // undo the 128B swizzle: logical chunk c
@@ -380,6 +404,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                         lo[4 * c + e] = __float_as_uint(__uint_as_float(w[e]) - __uint_as_float(hi[4 * c + e])) & 0xFFFFE000u;
                     }
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_free[land]);                    // the landing buffer is in registers: refill it
+                mbar_wait<true>(&empty[stage], phase ^ 1);                    // the stage's TMEM slot: MMAs of K-block g - STAGES retired
+                tc_fence_after();
                 const uint32_t dst = tmem_base + C::TMEM_A0 + stage * 64 + lane_addr;
                 tmem_st32(dst, hi);
                 tmem_st32(dst + 32, lo);
@@ -390,6 +418,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 if (warp == 2 && lane == 0) TL(gc, 6);
                 ++gc;
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                if (++land == C::LANDINGS) { land = 0; lphase ^= 1; }
             }
         }
     } else if (warp < 14) {
@@ -477,19 +506,36 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             if (warp == 6 && lane == 0) TL(g, 13);                            // tile prologue (params, residual prefetch) issued
             for (int kb = 0; kb < kblocks; ++kb, ++g) {
                 const uint32_t buf = g & 1;
-                mbar_wait<true>(&d_full[buf], (g >> 1) & 1);
+                if (p.exp_nolo & 16) mbar_wait<true>(&d_full[buf], (g >> 1) & 1);
+                else mbar_wait(&d_full[buf], (g >> 1) & 1);
                 if (warp == 6 && lane == 0) TL(g, 7);
                 tc_fence_after();
+                // software-pipelined drain in 16-column pieces: the load of piece i+1 is in flight while piece i is added;
+                // the buffer is handed back to the MMA issuer as soon as the last load has landed (before the last adds)
+                {
+                    const uint32_t src = tmem_base + buf * BN + lane_col;
+                    uint32_t va[16], vb[16];
+                    tmem_ld16_issue(src, va);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int cb = 0; cb < HALF / 32; ++cb) {
-                    float v[32];
-                    tmem_ld<32>(tmem_base + buf * BN + lane_col + cb * 32, v);
+                    for (int pc = 0; pc < HALF / 16; pc += 2) {
+                        if (pc + 1 < HALF / 16) tmem_ld16_issue(src + (pc + 1) * 16, vb);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[cb * 32 + j] += v[j];     // round-to-nearest fp32 running sum
+                        for (int j = 0; j < 16; ++j) acc[pc * 16 + j] += __uint_as_float(va[j]);   // round-to-nearest fp32 running sum
+                        if (pc + 1 < HALF / 16) {
+                            tmem_ld_wait();
+                            if (pc + 2 < HALF / 16) tmem_ld16_issue(src + (pc + 2) * 16, va);
+                            else {
+                                tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(&d_empty[buf]);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) acc[(pc + 1) * 16 + j] += __uint_as_float(vb[j]);
+                            if (pc + 2 < HALF / 16) tmem_ld_wait();
+                        }
+                    }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&d_empty[buf]);
                 if (warp == 6 && lane == 0) TL(g, 8);
                 if (kb == 0) after_first_kblock();
             }
