@@ -34,6 +34,7 @@
 #include <cuda.h>
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 #include "common.h"
@@ -445,31 +446,35 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         const bool dma = lane == 0 && quarter < CHUNKS;                       // this thread drives the TMA traffic of chunk `quarter`
         uint32_t g = 0, tile_par = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, tile_par ^= 1) {
-            const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
-            const int img = m_tile / tiles_per_img, rem = m_tile - img * tiles_per_img;
-            const int ho0 = (rem / p.tiles_x) * p.BH, wo0 = (rem % p.tiles_x) * BW;
-            const int n0 = n_tile * BN + half * HALF;                         // first channel of this group
+            // The tensor pipe is stalled at a tile boundary until this tile's first partial sums are drained, so nothing is
+            // computed up front: the tile coordinates are decoded after the first K-block's drain.
+            int img = 0, ho0 = 0, wo0 = 0, n0 = 0;
             auto out_pixel = [&](int r) -> int {                              // output pixel of this warp's row r, -1 = outside the image
                 const int prow = quarter * 32 + r;
                 const int ho = ho0 + (prow >> p.bw_log2), wo = wo0 + (prow & (BW - 1));
                 return (ho < p.Ho && wo < p.Wo) ? (img * p.Ho + ho) * p.Wo + wo : -1;
             };
-            // ---- the group's folded-BN scale/shift into shared memory, asynchronously, by the quarter-3 warp (arrays are
-            //      padded to cout_pad >= n0 + HALF): lanes [0, HALF/4) copy 16 bytes of scale, lanes [16, 16 + HALF/4) of shift.
-            //      Safe to overwrite: every warp of the group has passed the pre-store barrier of the previous tile.
-            if (quarter == 3) {
-                const int piece = lane & 15;
-                if (piece < HALF / 4) {
-                    const float* src = (lane < 16 ? p.scale : p.shift) + n0 + piece * 4;
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(par + (lane < 16 ? 0 : 4 * HALF) + piece * 16), "l"(src) : "memory");
-                }
-            }
-            // ---- after the first K-block: the previous tile's bulk stores have released the slab (waited for by the threads
-            //      that issued them), the params have landed; one group barrier publishes both, then the residual chunks
-            //      (128 pixels x 32 channels each) stream into the slab while the K loop runs.
+            // ---- after the first K-block: decode the tile; fetch the group's folded-BN scale/shift (arrays are padded to
+            //      cout_pad >= n0 + HALF) asynchronously - every warp of the group issues the same 16-byte copies (lanes
+            //      [0, HALF/4): scale, [16, 16 + HALF/4): shift) and later waits for its own, so no barrier has to publish
+            //      them; safe to overwrite: every warp has passed the pre-store barrier of the previous tile.  Then: the
+            //      previous tile's bulk stores have released the slab (waited for by the threads that issued them, published
+            //      by one group barrier), and the residual chunks (128 pixels x 32 channels each) stream into the slab while
+            //      the K loop runs.
             auto after_first_kblock = [&]() {
+                const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
+                img = m_tile / tiles_per_img;
+                const int rem = m_tile - img * tiles_per_img;
+                ho0 = (rem / p.tiles_x) * p.BH; wo0 = (rem % p.tiles_x) * BW;
+                n0 = n_tile * BN + half * HALF;                               // first channel of this group
+                {
+                    const int piece = lane & 15;
+                    if (piece < HALF / 4) {
+                        const float* src = (lane < 16 ? p.scale : p.shift) + n0 + piece * 4;
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(par + (lane < 16 ? 0 : 4 * HALF) + piece * 16), "l"(src) : "memory");
+                    }
+                }
                 if (dma) bulk_wait_read();
-                if (quarter == 3) asm volatile("cp.async.wait_all;" ::: "memory");
                 group_sync();
                 if (!has_res) return;
                 if (p.res_tma) {
@@ -541,21 +546,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             }
             // ---- fused epilogue (pixel per thread == TMEM lane, in place in the slab):
             //      y = post_scale * act(acc * scale + shift [+ res1]) [+ res2]
-            if (has_res) {
-                if (p.res_tma) mbar_wait(rbar, tile_par);
-                else asm volatile("cp.async.wait_all;" ::: "memory");         // this warp's own rows
-            }
+            asm volatile("cp.async.wait_all;" ::: "memory");                  // params (+ this warp's rows of a cp.async residual)
+            if (has_res && p.res_tma) mbar_wait(rbar, tile_par);
             __syncwarp();
             if (warp == 6 && lane == 0) TL(g - 1, 10);
-            {
-                // two 4-channel groups per step: their six shared-memory loads are in flight together (in-order issue,
-                // only two epilogue warps per scheduler to hide latency)
+            // two 4-channel groups per step: their six shared-memory loads are in flight together (in-order issue, only two
+            // epilogue warps per scheduler to hide latency).  SIMPLE = the ResNet/FPN/SSH form max(acc*scale+shift [+res], lo):
+            // half the instructions of the general form (RRDB: leaky, post-scale, post-activation residual).
+            auto phase1 = [&](auto simple_tag) {
+                constexpr bool SIMPLE = decltype(simple_tag)::value;
+                const float lo_clamp = neg_slope == 0.f ? 0.f : -INFINITY;    // relu | none
                 auto fuse = [&](const float a, const float sc, const float sh, const float rv) -> float {
                     float x = a * sc + sh;
-                    if (r_pre) x += rv;
-                    x = fmaxf(x, x * neg_slope) * post_scale;                 // act in {none, relu, leaky}: 0 <= neg_slope <= 1
-                    if (r_post) x += rv;
-                    return x;
+                    if constexpr (SIMPLE) {
+                        if (has_res) x += rv;
+                        return fmaxf(x, lo_clamp);
+                    } else {
+                        if (r_pre) x += rv;
+                        x = fmaxf(x, x * neg_slope) * post_scale;             // act in {none, relu, leaky}: 0 <= neg_slope <= 1
+                        if (r_post) x += rv;
+                        return x;
+                    }
                 };
 #pragma unroll
                 for (int j = 0; j < HALF; j += 8) {
@@ -572,7 +583,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     sts_f4(a0, x0);
                     sts_f4(a1, x1);
                 }
-            }
+            };
+            if (post_scale == 1.f && !r_post && (neg_slope == 0.f || neg_slope == 1.f)) phase1(std::true_type{});
+            else phase1(std::false_type{});
             if (warp == 6 && lane == 0) TL(g - 1, 11);
             if (p.out_tma) {
                 // ---- bulk tensor store of the slab (rows / channels outside the tensor are clipped by TMA)
