@@ -44,6 +44,7 @@ SIGNATURES = {
     "fcp_detect_post": (_i, [_p, _p, _i, _i, _i, _f, _f, _i, _i, _p, _p, _p, _p, _p, _p]),
     "fcp_align": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _i, _p, _i, _i, _i, _i, _p, _p, _p]),
     "fcp_align_list": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _i, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "fcp_as_batch": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "fcp_parse": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "fcp_parse_logits": (_i, [_p, _p, _i, _i, _i, _p]),
     "fcp_parse_tail": (_i, [_p, _p, _i, _i, _i, _p, _p]),
@@ -224,6 +225,26 @@ class Context:
             self.check(self.lib.fcp_align(self.h, _ptr(images), n, h, w, _ptr(pad), _ptr(idx), _ptr(lms), f, _ptr(tgt), ow, oh,
                                           bm, int(allow_skew), _ptr(crops), _ptr(mats), _ptr(valid)))
         return crops, mats, valid.astype(bool)
+
+    # ---- ingest
+    def as_batch(self, images, size=512, padding_mode="constant", out=None):
+        """``utils.as_batch`` (utils.py:273-342) on the device: list of u8 [h_i,w_i,3] arrays (or CUDA uint8 tensors) ->
+        (batch u8 [n,H,W,3], unscales f64 [n], paddings i64 [n,4]).  ``out``: optional preallocated batch (numpy array or
+        CUDA uint8 tensor), returned in place of a new numpy array."""
+        sw, sh = (int(size), int(size)) if isinstance(size, int) else (int(size[0]), int(size[1]))
+        imgs = [im if hasattr(im, "data_ptr") else np.ascontiguousarray(im, dtype=np.uint8) for im in images]
+        n = len(imgs)
+        for im in imgs:
+            if im.ndim != 3 or im.shape[2] != 3:
+                raise ValueError("as_batch expects HxWx3 uint8 images")
+        ptrs = (C.c_void_p * max(n, 1))(*[_ptr(im) for im in imgs])
+        hs = np.array([im.shape[0] for im in imgs], np.int32)
+        ws = np.array([im.shape[1] for im in imgs], np.int32)
+        batch = np.empty((n, sh, sw, 3), np.uint8) if out is None else out
+        unscales, pads = np.zeros(n, np.float64), np.zeros((n, 4), np.int32)
+        bm = BORDERS[padding_mode.lower()] if isinstance(padding_mode, str) else int(padding_mode)
+        self.check(self.lib.fcp_as_batch(self.h, C.cast(ptrs, _p), _ptr(hs), _ptr(ws), n, sw, sh, bm, _ptr(batch), _ptr(unscales), _ptr(pads)))
+        return batch, unscales, pads.astype(np.int64)
 
     # ---- parse
     def parse(self, crops):

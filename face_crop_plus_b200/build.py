@@ -10,10 +10,10 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libfcpb200.so"
-SOURCES = ["runtime.cu", "graphs.cu", "conv_ffma.cu", "conv_tc.cu", "misc.cu", "det_post.cu", "align.cu", "parse.cu"]
+SOURCES = ["runtime.cu", "graphs.cu", "conv_ffma.cu", "conv_tc.cu", "misc.cu", "det_post.cu", "align.cu", "parse.cu", "ingest.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-         "--expt-relaxed-constexpr", "-Xcompiler", "-Wall", "-Xcudafe", "--diag_suppress=177",
+         "--expt-relaxed-constexpr", "-Xcompiler", "-Wall", "-Xcompiler", "-ffp-contract=off", "-Xcudafe", "--diag_suppress=177",
          *os.environ.get("FCP_NVCC_FLAGS", "").split()]   # e.g. -DFCP_EXP_TIMELINE for the clock64 timeline build
 
 

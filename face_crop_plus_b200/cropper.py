@@ -123,7 +123,7 @@ class Cropper:
                 ldm_rows += rows.tolist()
             landmarks = self.landmarks[0][ldm_rows]
         else:
-            images, _, paddings = as_batch(images, self.resize_size)
+            images, _, paddings = as_batch(images, self.resize_size, ctx=self.ctx)
             if self.enh_model is None:
                 return self._process_detected_batch(images, paddings, file_names, output_dir)
             landmarks, indices = self.det_model.predict_u8(images)

@@ -152,6 +152,10 @@ int run_conv(fcp_ctx* ctx, const ConvOp& op);
 // (retinaface.py:450-451); mode 1: src = f32 NHWC 3-channel
 int launch_stem7(fcp_ctx* ctx, const void* src, int mode, int n, int h, int w, const float* w_kn /*[147][64]*/,
                  const float* scale, const float* shift, Tensor out);
+// batch ingest (utils.as_batch): resize (OpenCV INTER_AREA / INTER_CUBIC arithmetic) + centred padding of a ragged image list;
+// dev_ptrs[i] = device u8 [hs[i], ws[i], 3]; out = device u8 [n, size_h, size_w, 3]; unscales / paddings are HOST outputs
+int launch_ingest(fcp_ctx* ctx, const uint8_t* const* dev_ptrs, const int32_t* hs, const int32_t* ws, int n, int size_w,
+                  int size_h, int border_mode, uint8_t* out, double* unscales, int32_t* paddings);
 // conv 3x3/s1 with Cin=3 (RRDB conv_first): f32 NCHW input scaled by in_scale, + bias
 int launch_conv3_first(fcp_ctx* ctx, const float* src_nchw, float in_scale, int n, int h, int w, const float* w_kn,
                        const float* shift, Tensor out);

@@ -664,6 +664,27 @@ int fcp_align_list(fcp_ctx* ctx, const uint8_t* const* image_ptrs, const int32_t
                      border_mode, allow_skew, out_crops, out_matrices, out_valid);
 }
 
+int fcp_as_batch(fcp_ctx* ctx, const uint8_t* const* image_ptrs, const int32_t* hs, const int32_t* ws, int n, int size_w,
+                 int size_h, int border_mode, uint8_t* out_batch, double* out_unscales, int32_t* out_paddings) {
+    if (!ctx || n < 0 || size_w < 1 || size_h < 1 || border_mode < 0 || border_mode > 4 || (n && (!image_ptrs || !hs || !ws || !out_batch)))
+        return fail(ctx, FCP_ERR_INVALID, "fcp_as_batch: bad argument");
+    FCP_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n == 0) return FCP_OK;
+    std::vector<DevIn> imgs(n);
+    std::vector<const uint8_t*> dev_ptrs(n);
+    for (int i = 0; i < n; ++i) {
+        if (!image_ptrs[i] || hs[i] < 1 || ws[i] < 1) return fail(ctx, FCP_ERR_INVALID, "fcp_as_batch: empty image");
+        FCP_TRY(imgs[i].init(ctx, image_ptrs[i], (size_t)hs[i] * ws[i] * 3));
+        dev_ptrs[i] = imgs[i].as<uint8_t>();
+    }
+    DevOut out;
+    FCP_TRY(out.init(ctx, out_batch, (size_t)n * size_h * size_w * 3));
+    FCP_TRY(launch_ingest(ctx, dev_ptrs.data(), hs, ws, n, size_w, size_h, border_mode, out.as<uint8_t>(), out_unscales, out_paddings));
+    FCP_TRY(out.flush());
+    FCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FCP_OK;
+}
+
 int fcp_parse(fcp_ctx* ctx, const uint8_t* crops, int f, int h, int w, uint8_t* out_labels, int32_t* out_hist) {
     FCP_TRY(need_model(ctx, FCP_MODEL_BISENET));
     if (f < 0 || h < 1 || w < 1 || (f && !crops)) return fail(ctx, FCP_ERR_INVALID, "fcp_parse: bad argument");

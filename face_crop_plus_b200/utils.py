@@ -1,7 +1,7 @@
 """Host-side helpers on either side of the hot path (file I/O, batching, landmark files).
 
 These mirror ``face_crop_plus/utils.py`` in behaviour (same function names and return conventions) but are plain
-host code: decoding/encoding and the resize+pad batching are *outside* the accelerated path.
+host code for decoding/encoding and landmark files; ``as_batch`` runs on the GPU through ``fcp_as_batch``.
 """
 from __future__ import annotations
 
@@ -71,27 +71,13 @@ def read_images(file_names, input_dir: str):
     return images, np.array(file_names)[[i for i, n in enumerate(file_names) if n in set(kept)]] if kept else np.array([], dtype=str)
 
 
-def as_batch(images, size=512, padding_mode: str = "constant"):
+def as_batch(images, size=512, padding_mode: str = "constant", ctx=None):
     """Aspect-preserving resize to fit ``size`` (w, h) + centred padding; returns (batch u8 [N,H,W,3], unscales, paddings
-    [N,4] = top,bottom,left,right) exactly like utils.py:273-342 (INTER_AREA when shrinking, INTER_CUBIC otherwise)."""
-    import cv2
-    size = (size, size) if isinstance(size, int) else tuple(size)
-    border = getattr(cv2, f"BORDER_{padding_mode.upper()}")
-    batch, unscales, paddings = [], [], []
-    for img in images:
-        h, w = img.shape[:2]
-        interp = cv2.INTER_AREA if max(h, w) > max(size) else cv2.INTER_CUBIC
-        rw, rh = size[0] / w, size[1] / h
-        if rw < rh:
-            scale, new_w, new_h = rw, size[0], int(h * rw)
-            gap = size[1] - new_h
-            pad = [gap // 2, (gap + 1) // 2, 0, 0]
-        else:
-            scale, new_w, new_h = rh, int(w * rh), size[1]
-            gap = size[0] - new_w
-            pad = [0, 0, gap // 2, (gap + 1) // 2]
-        out = cv2.copyMakeBorder(cv2.resize(img, (new_w, new_h), interpolation=interp), *pad, borderType=border)
-        batch.append(out)
-        unscales.append(np.array(scale))
-        paddings.append(np.array(pad))
-    return np.stack(batch), np.stack(unscales), np.stack(paddings)
+    [N,4] = top,bottom,left,right) exactly like utils.py:273-342 (INTER_AREA when shrinking, INTER_CUBIC otherwise).
+
+    Runs on the GPU (``fcp_as_batch``: OpenCV's INTER_AREA / INTER_CUBIC / copyMakeBorder arithmetic restated in
+    ``csrc/ingest.cu``); ``ctx`` is the :class:`_abi.Context` to use (default: the context of cuda:0)."""
+    if ctx is None:
+        from .models import get_context
+        ctx = get_context("cuda:0")
+    return ctx.as_batch(images, size, padding_mode)

@@ -73,6 +73,16 @@ int fcp_profile_read(fcp_ctx* ctx, double* out4);
 int fcp_load_tensor(fcp_ctx* ctx, int model, const char* key, const float* host_data, const int64_t* shape, int ndim);
 int fcp_finalize(fcp_ctx* ctx, int model, int rrdb_blocks);
 
+/* ---- ingest: replaces utils.as_batch (utils.py:273-342) ------------------------------------------------
+ * image_ptrs[i] u8 [hs[i],ws[i],3] RGB (host or device).  Every image is resized to fit (size_w, size_h) keeping its
+ * aspect ratio - OpenCV's INTER_AREA arithmetic when max(h,w) > max(size), its INTER_CUBIC arithmetic otherwise, a plain
+ * copy when the size already fits (utils.py:320,334) - and centred with copyMakeBorder semantics (utils.py:335;
+ * border_mode = FCP_BORDER_*).  out_batch u8 [n,size_h,size_w,3] (host or device); out_unscales f64 [n] and
+ * out_paddings i32 [n,4] = (top,bottom,left,right) are HOST arrays (either may be NULL). */
+int fcp_as_batch(fcp_ctx* ctx, const uint8_t* const* image_ptrs, const int32_t* hs, const int32_t* ws, int n,
+                 int size_w, int size_h, int border_mode, uint8_t* out_batch, double* out_unscales,
+                 int32_t* out_paddings);
+
 /* ---- detect: replaces RetinaFace.predict (models/retinaface.py:410-470) ---------------------------------
  * images  u8 [n,h,w,3] RGB (what utils.as_batch produces, before as_tensor's float conversion; h,w % 32 == 0 not
  *         required).  Outputs, ordered by image then by the strategy's order, capacity max_faces:
