@@ -71,6 +71,17 @@ def read_images(file_names, input_dir: str):
     return images, np.array(file_names)[[i for i, n in enumerate(file_names) if n in set(kept)]] if kept else np.array([], dtype=str)
 
 
+def batch_plan(h: int, w: int, size) -> tuple[int, int, float, list[int]]:
+    """Geometry of utils.py:317-331 for one image: (new_w, new_h, unscale, [top, bottom, left, right])."""
+    size = (size, size) if isinstance(size, int) else tuple(size)
+    rw, rh = size[0] / w, size[1] / h
+    if rw < rh:
+        new_w, new_h, unscale = size[0], int(h * rw), rw
+        return new_w, new_h, unscale, [(size[1] - new_h) // 2, (size[1] - new_h + 1) // 2, 0, 0]
+    new_w, new_h, unscale = int(w * rh), size[1], rh
+    return new_w, new_h, unscale, [0, 0, (size[0] - new_w) // 2, (size[0] - new_w + 1) // 2]
+
+
 def as_batch(images, size=512, padding_mode: str = "constant", ctx=None):
     """Aspect-preserving resize to fit ``size`` (w, h) + centred padding; returns (batch u8 [N,H,W,3], unscales, paddings
     [N,4] = top,bottom,left,right) exactly like utils.py:273-342 (INTER_AREA when shrinking, INTER_CUBIC otherwise).

@@ -76,6 +76,16 @@ def test_full_size_properties(ctx):
     assert abs(inner.mean() - d.mean()) < 0.5                                   # area averaging preserves the mean
 
 
+def test_as_batch_geometry_matches_host_plan(ctx):
+    from face_crop_plus_b200 import utils
+    shapes = [(100, 200), (300, 150), (64, 64), (77, 1000)]
+    batch, unscales, pads = utils.as_batch(_rand_images(shapes, 2), (128, 96), ctx=ctx)
+    assert batch.shape == (4, 96, 128, 3)
+    for (h, w), u, p in zip(shapes, unscales, pads):
+        _, _, unscale, pad = utils.batch_plan(h, w, (128, 96))
+        assert u == unscale and p.tolist() == pad
+
+
 def test_as_batch_errors(ctx):
     from face_crop_plus_b200 import _abi
     with pytest.raises(ValueError):

@@ -16,15 +16,13 @@ def test_landmark_slices():
         landmarks_target((256, 256), 0.65, 4)
 
 
-def test_as_batch_geometry():
-    pytest.importorskip("cv2")
-    imgs = [np.zeros((100, 200, 3), np.uint8), np.zeros((300, 150, 3), np.uint8), np.zeros((64, 64, 3), np.uint8)]
-    batch, unscales, pads = utils.as_batch(imgs, (128, 96))
-    assert batch.shape == (3, 96, 128, 3)
-    assert pads.tolist() == [[16, 16, 0, 0], [0, 0, 40, 40], [0, 0, 16, 16]]
-    np.testing.assert_allclose(unscales, [0.64, 0.32, 1.5])
-    same, _, pads = utils.as_batch([synth.make_images(1, 64, 64)[0]], 64)       # identity at the native size
-    assert np.array_equal(same[0], synth.make_images(1, 64, 64)[0]) and not pads.any()
+def test_batch_plan_geometry():
+    """utils.py:317-331; the resize + padding itself runs on the GPU (tests/test_gpu_ingest.py)."""
+    plans = [utils.batch_plan(h, w, (128, 96)) for h, w in [(100, 200), (300, 150), (64, 64)]]
+    assert [p[3] for p in plans] == [[16, 16, 0, 0], [0, 0, 40, 40], [0, 0, 16, 16]]
+    assert [p[:2] for p in plans] == [(128, 64), (48, 96), (96, 96)]
+    np.testing.assert_allclose([p[2] for p in plans], [0.64, 0.32, 1.5])
+    assert utils.batch_plan(64, 64, 64) == (64, 64, 1.0, [0, 0, 0, 0])          # identity at the native size (SURVEY §8 a2)
 
 
 def test_enhance_gate_matches_oracle():
