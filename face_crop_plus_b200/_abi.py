@@ -49,6 +49,7 @@ SIGNATURES = {
     "fcp_parse_logits": (_i, [_p, _p, _i, _i, _i, _p]),
     "fcp_parse_tail": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "fcp_masks": (_i, [_p, _p, _i, _i, _i, _p, _p]),
+    "fcp_group": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _i, _i, _i, _p, _i, _i, _p, _p, _p]),
     "fcp_enhance": (_i, [_p, _p, _i, _i, _i, _p]),
     "fcp_enhance_forward": (_i, [_p, _p, _i, _i, _i, _p]),
     "fcp_pipeline": (_i, [_p, _p, _i, _i, _i, _p, _f, _f, _i, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
@@ -276,6 +277,27 @@ class Context:
         out = np.empty((f, h, w), np.uint8)
         self.check(self.lib.fcp_masks(self.h, _ptr(labels), f, h, w, _ptr(lut), _ptr(out)))
         return out
+
+    def group(self, labels, hist, attr_groups=None, mask_groups=None, attr_threshold=5, mask_threshold=10, join_and=True,
+              want_masks=True):
+        """Device-side ``group_by_attributes`` / ``group_by_masks`` (bise.py:214-325).  labels u8 [f,h,w] and hist i32 [f,19]
+        may be numpy arrays or CUDA tensors.  Returns (attr_member bool [n_attr,f], mask_member bool [n_mask,f],
+        masks u8 [n_mask,f,h,w] or None), rows in the dictionaries' key order."""
+        f, h, w = labels.shape
+        attr_lists = [list(v) for v in (attr_groups or {}).values()]
+        mask_lists = [list(v) for v in (mask_groups or {}).values()]
+        n_attr, n_mask = len(attr_lists), len(mask_lists)
+        codes = np.array([a for v in attr_lists for a in v] or [0], np.int32)
+        offs = np.cumsum([0] + [len(v) for v in attr_lists]).astype(np.int32)
+        lut = np.zeros((max(n_mask, 1), 19), np.uint8)
+        for m, v in enumerate(mask_lists):
+            lut[m, [c for c in v if 0 <= c < 19]] = 1
+        out_attr, out_mask = np.zeros((n_attr, f), np.uint8), np.zeros((n_mask, f), np.uint8)
+        masks = np.empty((n_mask, f, h, w), np.uint8) if (want_masks and n_mask) else None
+        self.check(self.lib.fcp_group(self.h, _ptr(labels), _ptr(hist), f, h, w, _ptr(codes), _ptr(offs), n_attr, int(attr_threshold),
+                                      int(bool(join_and)), _ptr(lut), n_mask, int(mask_threshold), _ptr(out_attr), _ptr(out_mask),
+                                      _ptr(masks)))
+        return out_attr.astype(bool), out_mask.astype(bool), masks
 
     # ---- enhance
     def enhance(self, images_nchw, gate=None):

@@ -195,6 +195,10 @@ int launch_parse_prep(fcp_ctx* ctx, const uint8_t* crops, int f, int h, int w, f
 int launch_parse_tail(fcp_ctx* ctx, const float* logits, int layout_nhwc, int cs, int f, int fh, int fw, int h, int w,
                       uint8_t* labels, int32_t* hist);
 int launch_masks(fcp_ctx* ctx, const uint8_t* labels, size_t count, const uint8_t* lut_dev, uint8_t* out);
+// grouping rules of bise.py:214-325 on the per-class histogram; all mask groups' 0/255 images in one pass over the labels
+int launch_group(fcp_ctx* ctx, const int32_t* hist, int f, const int32_t* codes, const int32_t* offs, int n_attr, int attr_thr,
+                 int join_and, const uint8_t* lut, int n_mask, int mask_thr, uint8_t* out_attr, uint8_t* out_mask);
+int launch_multi_masks(fcp_ctx* ctx, const uint8_t* labels, size_t count, const uint8_t* lut_dev, int n_mask, uint8_t* out);
 int launch_upsample2x(fcp_ctx* ctx, Tensor in, Tensor out);   // out = nearest x2 upsample of in
 int launch_nhwc_to_nchw(fcp_ctx* ctx, const float* in, int n, int h, int w, int c, int cs, float* out);
 

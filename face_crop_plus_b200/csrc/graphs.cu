@@ -762,6 +762,38 @@ static int enhance_core(fcp_ctx* ctx, const float* x, float in_div, int n, int h
     return FCP_OK;
 }
 
+int fcp_group(fcp_ctx* ctx, const uint8_t* labels, const int32_t* hist, int f, int h, int w, const int32_t* attr_codes,
+              const int32_t* attr_offsets, int n_attr, int attr_threshold, int join_and, const uint8_t* mask_lut, int n_mask,
+              int mask_threshold, uint8_t* out_attr, uint8_t* out_mask, uint8_t* out_masks) {
+    if (!ctx || f < 0 || n_attr < 0 || n_mask < 0 || n_mask > 32 || (f && !hist) || (n_attr && (!attr_codes || !attr_offsets || !out_attr)) ||
+        (n_mask && (!mask_lut || !out_mask)) || (out_masks && (!labels || h < 1 || w < 1)))
+        return fail(ctx, FCP_ERR_INVALID, "fcp_group: bad argument");
+    FCP_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (f == 0 || n_attr + n_mask == 0) return FCP_OK;
+    if (n_attr && is_device_ptr(attr_offsets)) return fail(ctx, FCP_ERR_INVALID, "fcp_group: attr_offsets must be host memory");
+    const int n_codes = n_attr ? attr_offsets[n_attr] : 0;
+    DevIn hs, codes, offs, lut, lab;
+    FCP_TRY(hs.init(ctx, hist, sizeof(int32_t) * 19 * f));
+    FCP_TRY(codes.init(ctx, attr_codes, sizeof(int32_t) * (n_codes > 0 ? n_codes : 1)));
+    FCP_TRY(offs.init(ctx, attr_offsets, sizeof(int32_t) * (n_attr + 1)));
+    FCP_TRY(lut.init(ctx, mask_lut, (size_t)19 * (n_mask > 0 ? n_mask : 1)));
+    DevOut oa, om, omasks;
+    FCP_TRY(oa.init(ctx, out_attr, (size_t)n_attr * f));
+    FCP_TRY(om.init(ctx, out_mask, (size_t)n_mask * f));
+    FCP_TRY(launch_group(ctx, hs.as<int32_t>(), f, codes.as<int32_t>(), offs.as<int32_t>(), n_attr, attr_threshold, join_and,
+                         lut.as<uint8_t>(), n_mask, mask_threshold, oa.as<uint8_t>(), om.as<uint8_t>()));
+    if (out_masks && n_mask) {
+        const size_t count = (size_t)f * h * w;
+        FCP_TRY(lab.init(ctx, labels, count));
+        FCP_TRY(omasks.init(ctx, out_masks, count * n_mask));
+        FCP_TRY(launch_multi_masks(ctx, lab.as<uint8_t>(), count, lut.as<uint8_t>(), n_mask, omasks.as<uint8_t>()));
+        FCP_TRY(omasks.flush());
+    }
+    FCP_TRY(oa.flush()); FCP_TRY(om.flush());
+    FCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FCP_OK;
+}
+
 int fcp_enhance(fcp_ctx* ctx, float* images, int n, int h, int w, const uint8_t* do_enhance) {
     FCP_TRY(need_model(ctx, FCP_MODEL_RRDBNET));
     if (!images || n < 1 || h < 1 || w < 1) return fail(ctx, FCP_ERR_INVALID, "fcp_enhance: bad argument");

@@ -124,6 +124,59 @@ __global__ void masks_kernel(const uint8_t* __restrict__ labels, size_t count, c
     }
 }
 
+// group_by_attributes / group_by_masks membership (bise.py:214-325) from the per-class pixel histogram: integer compares.
+//   attribute group g = codes[offs[g] .. offs[g+1]) of signed class ids: a > 0 -> count(|a|) > thr, else count(|a|) <= thr,
+//   joined by AND (attr_join_by_and) or OR;  mask group m: sum of hist over the classes with lut[m][c] != 0 > mask_thr.
+__global__ void group_kernel(const int32_t* __restrict__ hist, int f, const int32_t* __restrict__ codes,
+                             const int32_t* __restrict__ offs, int n_attr, int attr_thr, int join_and,
+                             const uint8_t* __restrict__ lut, int n_mask, int mask_thr, uint8_t* __restrict__ out_attr,
+                             uint8_t* __restrict__ out_mask) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= f * (n_attr + n_mask)) return;
+    const int g = idx / f, face = idx - g * f;
+    const int32_t* h = hist + face * 19;
+    if (g < n_attr) {
+        bool all = true, any = false;
+        for (int e = offs[g]; e < offs[g + 1]; ++e) {
+            const int a = codes[e], c = a < 0 ? -a : a;
+            const int cnt = c < 19 ? h[c] : 0;
+            const bool t = a > 0 ? cnt > attr_thr : cnt <= attr_thr;
+            all &= t; any |= t;
+        }
+        out_attr[g * f + face] = (join_and ? all : any) ? 1 : 0;
+    } else {
+        const int m = g - n_attr;
+        int sum = 0;
+        for (int c = 0; c < 19; ++c) sum += lut[m * 19 + c] ? h[c] : 0;
+        out_mask[m * f + face] = sum > mask_thr ? 1 : 0;
+    }
+}
+
+// all mask groups in one pass over the labels: out[m][i] = 255 where lut[m][label[i]] != 0   (n_mask <= 32)
+__global__ void multi_masks_kernel(const uint8_t* __restrict__ labels, size_t count, const uint8_t* __restrict__ lut, int n_mask,
+                                   uint8_t* __restrict__ out) {
+    __shared__ uint32_t bits[32];                         // bits[class] = set of groups containing the class
+    if (threadIdx.x < 32) {
+        uint32_t b = 0;
+        if (threadIdx.x < 19)
+            for (int m = 0; m < n_mask; ++m) b |= lut[m * 19 + threadIdx.x] ? (1u << m) : 0u;
+        bits[threadIdx.x] = b;
+    }
+    __syncthreads();
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= count) return;
+    if (i + 3 < count) {
+        const uchar4 v = *reinterpret_cast<const uchar4*>(labels + i);
+        const uint32_t b0 = bits[v.x & 31], b1 = bits[v.y & 31], b2 = bits[v.z & 31], b3 = bits[v.w & 31];
+        for (int m = 0; m < n_mask; ++m)
+            *reinterpret_cast<uchar4*>(out + (size_t)m * count + i) =
+                make_uchar4((b0 >> m) & 1 ? 255 : 0, (b1 >> m) & 1 ? 255 : 0, (b2 >> m) & 1 ? 255 : 0, (b3 >> m) & 1 ? 255 : 0);
+    } else {
+        for (size_t j = i; j < count; ++j)
+            for (int m = 0; m < n_mask; ++m) out[(size_t)m * count + j] = (bits[labels[j] & 31] >> m) & 1 ? 255 : 0;
+    }
+}
+
 // x4: NHWC [n,4h,4w,cs] (3 valid channels) -> out NCHW [n,3,h,w] (image i at out + i*3*h*w)
 __global__ void rrdb_tail_kernel(const float* __restrict__ x4, int cs, int co, int n, int h, int w,
                                  float* __restrict__ out) {
@@ -178,6 +231,24 @@ int launch_masks(fcp_ctx* ctx, const uint8_t* labels, size_t count, const uint8_
     if (count == 0) return FCP_OK;
     size_t threads = (count + 3) / 4;
     masks_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(labels, count, lut_dev, out);
+    FCP_KERNEL_CHECK(ctx);
+    return FCP_OK;
+}
+
+int launch_group(fcp_ctx* ctx, const int32_t* hist, int f, const int32_t* codes, const int32_t* offs, int n_attr, int attr_thr,
+                 int join_and, const uint8_t* lut, int n_mask, int mask_thr, uint8_t* out_attr, uint8_t* out_mask) {
+    const int total = f * (n_attr + n_mask);
+    if (total == 0) return FCP_OK;
+    group_kernel<<<(total + 127) / 128, 128, 0, ctx->stream>>>(hist, f, codes, offs, n_attr, attr_thr, join_and, lut, n_mask, mask_thr,
+                                                              out_attr, out_mask);
+    FCP_KERNEL_CHECK(ctx);
+    return FCP_OK;
+}
+
+int launch_multi_masks(fcp_ctx* ctx, const uint8_t* labels, size_t count, const uint8_t* lut_dev, int n_mask, uint8_t* out) {
+    if (count == 0 || n_mask == 0) return FCP_OK;
+    const size_t threads = (count + 3) / 4;
+    multi_masks_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(labels, count, lut_dev, n_mask, out);
     FCP_KERNEL_CHECK(ctx);
     return FCP_OK;
 }

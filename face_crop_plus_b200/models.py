@@ -153,25 +153,23 @@ class BiSeNet(LoadMixin):
         self.std = [0.229, 0.224, 0.225]
 
     def groups_from(self, labels: np.ndarray, hist: np.ndarray):
-        """Grouping rules of bise.py:214-325,407-416, evaluated on the per-class pixel histogram the kernel emits."""
+        """Grouping rules of bise.py:214-325,407-416: membership flags and the 0/255 mask images come from the device
+        (``fcp_group``: integer compares on the per-class histogram, one pass over the labels for all mask groups)."""
         attr_groups = mask_groups = None
+        if len(hist) == 0:
+            return ({} if self.attr_groups is not None else None), ({} if self.mask_groups is not None else None)
+        with _lock:
+            attr_m, mask_m, masks = self.ctx.group(np.ascontiguousarray(labels), np.ascontiguousarray(hist, dtype=np.int32),
+                                                   self.attr_groups, self.mask_groups, self.attr_threshold, self.mask_threshold,
+                                                   self.attr_join_by_and)
         if self.attr_groups is not None:
-            join = np.all if self.attr_join_by_and else np.any
-            attr_groups = {}
-            for k, v in self.attr_groups.items():
-                tests = [hist[:, abs(a)] > self.attr_threshold if a > 0 else hist[:, abs(a)] <= self.attr_threshold for a in v]
-                idx = np.nonzero(join(np.stack(tests, 1), 1))[0].tolist() if len(hist) else []
-                if idx:
-                    attr_groups[k] = idx
+            attr_groups = {k: np.nonzero(attr_m[g])[0].tolist() for g, k in enumerate(self.attr_groups) if attr_m[g].any()}
         if self.mask_groups is not None:
             mask_groups = {}
-            for k, v in self.mask_groups.items():
-                classes = [c for c in v if 0 <= c < 19]
-                idx = np.nonzero(hist[:, classes].sum(1) > self.mask_threshold)[0].tolist() if len(hist) else []
-                if idx:
-                    with _lock:
-                        masks = self.ctx.masks(np.ascontiguousarray(labels[idx]), classes)
-                    mask_groups[k] = (idx, masks)
+            for m, k in enumerate(self.mask_groups):
+                idx = np.nonzero(mask_m[m])[0].tolist()
+                if idx:                                                        # empty groups are dropped (bise.py:407-416)
+                    mask_groups[k] = (idx, masks[m][idx])
         return attr_groups, mask_groups
 
     def predict_u8(self, crops_u8_nhwc: np.ndarray):

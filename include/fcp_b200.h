@@ -126,6 +126,18 @@ int fcp_parse_logits(fcp_ctx* ctx, const uint8_t* crops, int f, int h, int w, fl
 int fcp_parse_tail(fcp_ctx* ctx, const float* logits, int f, int h, int w, uint8_t* out_labels, int32_t* out_hist);
 int fcp_masks(fcp_ctx* ctx, const uint8_t* labels, int f, int h, int w, const uint8_t* class_lut19, uint8_t* out_masks);
 
+/* grouping: replaces BiSeNet.group_by_attributes / group_by_masks (bise.py:214-325) - integer work on the histogram and
+ * the labels, no host round trip.  hist i32 [f,19], labels u8 [f,h,w] (only read when out_masks != NULL).
+ * Attribute group g = attr_codes[attr_offsets[g] .. attr_offsets[g+1]) (signed class ids as in Cropper(attr_groups=...):
+ * a > 0: more than attr_threshold pixels of class a; otherwise at most attr_threshold pixels of class |a|), joined by AND
+ * when join_and != 0 (attr_join_by_and, bise.py:184), else OR.  Mask group m = the classes c with mask_lut[m*19+c] != 0;
+ * a face belongs to it when more than mask_threshold pixels fall into those classes (bise.py:316).  n_mask <= 32.
+ * out_attr u8 [n_attr,f], out_mask u8 [n_mask,f] membership flags; out_masks u8 [n_mask,f,h,w] = 0/255 for EVERY face
+ * (NULL = skip; the caller keeps the members, like mask[inds] at bise.py:317). */
+int fcp_group(fcp_ctx* ctx, const uint8_t* labels, const int32_t* hist, int f, int h, int w, const int32_t* attr_codes,
+              const int32_t* attr_offsets, int n_attr, int attr_threshold, int join_and, const uint8_t* mask_lut,
+              int n_mask, int mask_threshold, uint8_t* out_attr, uint8_t* out_mask, uint8_t* out_masks);
+
 /* ---- enhance: replaces RRDBNet.predict / forward (models/rrdb.py:64-146) --------------------------------
  * images f32 [n,3,h,w] NCHW, 0..255 (the tensor Cropper hands over, cropper.py:835); enhanced IN PLACE where
  * do_enhance[i] != 0 (gate computed by the host from landmarks, rrdb.py:125-140; NULL = all). */
