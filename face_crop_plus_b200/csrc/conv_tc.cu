@@ -27,7 +27,7 @@
 // CTA = 15 warps, persistent over output tiles (128 pixels x BN channels):
 //   warp 0      TMA producer          full_a[l] <- A bytes (waits a_free[l]);  full_b[s] <- weight bytes (waits empty[s])
 //   warps 2-5   hi/lo converters      a_free[l], conv[s] <- 4 arrivals (1/warp) (wait full_a[l], then empty[s] for the TMEM slot)
-//   warps 1,14  MMA issuers (1 lane each, alternating K-blocks)  empty[s], d_full[b] <- tcgen05.commit (wait conv[s], full_b[s], d_empty[b])
+//   warps 1,14,(15: BN=64)  MMA issuers (1 lane each, K-blocks round-robin, one partial-sum buffer each)  empty[s], d_full[b] <- tcgen05.commit (wait conv[s], full_b[s], d_empty[b])
 //   warps 6-13  accumulate+epilogue   d_empty[b] <- 8 arrivals (1/warp) (wait d_full[b]); per K-block TMEM -> regs (+=),
 //               after the last K-block: fused epilogue -> HBM.  Warp w owns TMEM lanes 32*(w%4).. and half of the columns.
 // Two TMEM partial-sum buffers let the drain of K-block i overlap the MMAs of K-block i+1.
@@ -46,11 +46,12 @@ namespace {
 constexpr int TILE_M = 128;
 constexpr int KB = 32;                         // channels per K-block (128 bytes of fp32)
 constexpr int A_TILE_BYTES = TILE_M * KB * 4;  // 16 KiB
-// MMA-issuing warps (warp 1 and warp 14).  Must stay 2: each partial-sum buffer (g & 1) then has exactly one issuer, so a
-// parity wait on d_empty can never be more than one phase ahead (with 3 issuers the same buffer is touched out of
-// order and mbarrier parity waits alias -> corrupted sums and a deadlock; measured the hard way).
-constexpr int NUM_ISSUERS = 2;
-constexpr int NUM_THREADS = 32 * (14 + NUM_ISSUERS - 1);
+// MMA-issuing warps: warp 1, warp 14 and (BN = 64 only) warp 15, one lane each, K-blocks round-robin.  Invariant: there
+// are exactly as many partial-sum buffers in tensor memory as issuers and issuer i only ever writes buffer i, so a parity
+// wait on d_empty can never be more than one phase ahead (3 issuers sharing 2 buffers touch a buffer out of order and
+// the mbarrier parity waits alias -> corrupted sums and a deadlock; measured the hard way).
+constexpr int MAX_ISSUERS = 3;
+constexpr int NUM_THREADS = 32 * (14 + MAX_ISSUERS - 1);
 
 struct alignas(64) TcParams {
     CUtensorMap tmA[4];                        // input, one per (row parity, column parity); stride 1 uses [0]
@@ -242,10 +243,13 @@ template <int BN> struct Cfg {
     // retire ~ 3300 cycles, measured) divided by its depth, not by any bandwidth.  The fp32 A tile only lives from its
     // landing to its conversion, so it gets its own short ring (LANDINGS); a pipeline STAGE is a weight slot in shared
     // memory plus an (a_hi | a_lo) slot in tensor memory, both held until the K-block's MMAs retire.
-    static constexpr int STAGES = BN >= 128 ? 4 : (BN == 64 ? 6 : 7);
+    static constexpr int STAGES = BN >= 128 ? 4 : (BN == 64 ? 5 : 7);
     static constexpr int LANDINGS = BN >= 128 ? 2 : 3;
-    // tensor memory: [0, 2*BN) two partial-sum buffers; then STAGES x (a_hi 32 cols | a_lo 32 cols)
-    static constexpr int TMEM_A0 = 2 * BN;
+    // One tcgen05.mma costs its issuing thread ~85 cycles whatever N is, so the narrow BN = 64 tiles (32-cycle MMAs) are
+    // issue-bound: they get a third issuer + accumulator and one stage less (tensor memory is 512 columns).
+    static constexpr int ISSUERS = BN == 64 ? 3 : 2;
+    // tensor memory: [0, ISSUERS*BN) partial-sum buffers; then STAGES x (a_hi 32 cols | a_lo 32 cols)
+    static constexpr int TMEM_A0 = ISSUERS * BN;
     static constexpr int TMEM_COLS = 512;
     static_assert(TMEM_A0 + STAGES * 64 <= TMEM_COLS, "tensor memory budget");
     static constexpr int EPI_WARPS = BN >= 64 ? 8 : 4;                    // BN=32: one warp per TMEM lane quarter
@@ -275,11 +279,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     uint64_t* empty = bars + 2 * C::STAGES;        // [STAGES]   the K-block's MMAs have retired: weight slot + TMEM slot reusable
     uint64_t* full_a = bars + 3 * C::STAGES;       // [LANDINGS] fp32 A tile has landed
     uint64_t* a_free = full_a + C::LANDINGS;       // [LANDINGS] the converters have read the landing buffer
-    uint64_t* d_full = a_free + C::LANDINGS;       // [2]  partial sum of one K-block is complete in TMEM buffer b
-    uint64_t* d_empty = d_full + 2;                // [2]  buffer b has been drained to registers
-    uint64_t* res_bar = d_empty + 2;               // [2]  (first GROUPS used) residual chunks of the group's tile have landed
+    uint64_t* d_full = a_free + C::LANDINGS;       // [ISSUERS]  partial sum of one K-block is complete in TMEM buffer b
+    uint64_t* d_empty = d_full + C::ISSUERS;       // [ISSUERS]  buffer b has been drained to registers
+    uint64_t* res_bar = d_empty + C::ISSUERS;      // [2]  (first GROUPS used) residual chunks of the group's tile have landed
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(res_bar + 2);
-    static_assert((3 * C::STAGES + 2 * C::LANDINGS + 6) * 8 + 4 <= 512, "barrier area");
+    static_assert((3 * C::STAGES + 2 * C::LANDINGS + 2 * C::ISSUERS + 2) * 8 + 4 <= 512, "barrier area");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto stage_b_hi = [&](int s) { return smem + s * C::B_SLOT_BYTES; };
@@ -289,7 +293,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_b[s], 1); mbar_init(&conv[s], 4); mbar_init(&empty[s], 1); }
         for (int l = 0; l < C::LANDINGS; ++l) { mbar_init(&full_a[l], 1); mbar_init(&a_free[l], 4); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&d_full[a], 1); mbar_init(&d_empty[a], C::EPI_WARPS); mbar_init(&res_bar[a], C::CHUNKS); }
+        for (int a = 0; a < C::ISSUERS; ++a) { mbar_init(&d_full[a], 1); mbar_init(&d_empty[a], C::EPI_WARPS); }
+        for (int a = 0; a < 2; ++a) mbar_init(&res_bar[a], C::CHUNKS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_base_smem, C::TMEM_COLS);
@@ -338,26 +343,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             }
         }
     } else if (warp == 1 || warp >= 14) {
-        // ============================================================== MMA issuers (warp 1: even K-blocks, warp 14: odd)
-        if (lane == 0) {
+        // ============================================================== MMA issuers (warps 1, 14, 15: K-blocks round-robin)
+        const uint32_t me = warp == 1 ? 0u : (uint32_t)(warp - 13);
+        if (lane == 0 && me < (uint32_t)C::ISSUERS) {
             // instruction descriptor: D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10), both K-major, N>>3 at bit 17, M>>4 at bit 24
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
             // Issuing a tcgen05.mma blocks the thread for about its execution time, and every barrier wait costs a few
-            // hundred cycles; with a single issuer the tensor pipe idled ~40% of each K-block.  NUM_ISSUERS threads take
-            // K-blocks round-robin, so one thread's waits overlap the others' MMAs.
-            const uint32_t me = warp == 1 ? 0u : (uint32_t)(warp - 13);
+            // hundred cycles; with a single issuer the tensor pipe idled ~40% of each K-block.  ISSUERS threads take
+            // K-blocks round-robin, so one thread's waits overlap the others' MMAs.  Issuer i owns partial-sum buffer i.
             uint32_t g = 0;                                                   // K-blocks so far (all tiles)
+            uint32_t turn = 0, mine = 0;                                      // g % ISSUERS; K-blocks this thread has issued
             int stage = 0; uint32_t phase = 0;
+            const uint32_t buf = me;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 for (int kb = 0; kb < kblocks; ++kb, ++g) {
-                    if (g % NUM_ISSUERS == me) {
-                        const uint32_t buf = g & 1;
+                    if (turn == me) {
                         // operands first (normally long complete), the partial-sum buffer last: its release by the drain
                         // warps is the critical dependency of this thread's K-block chain
                         mbar_wait(&full_b[stage], phase);                     // weights landed
                         mbar_wait(&conv[stage], phase);                       // a_hi | a_lo converted into the stage's TMEM slot
                         TL(g, 3);
-                        mbar_wait(&d_empty[buf], ((g >> 1) & 1) ^ 1);         // partial-sum buffer drained
+                        mbar_wait(&d_empty[buf], (mine & 1) ^ 1);             // partial-sum buffer drained
                         TL(g, 2);
                         tc_fence_after();
                         const uint32_t d_tmem = tmem_base + buf * BN;
@@ -375,7 +381,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                         umma_commit(&empty[stage]);                           // smem slot + TMEM A slot reusable once these MMAs retire
                         umma_commit(&d_full[buf]);                            // partial sum of this K-block complete
                         TL(g, 4);
+                        ++mine;
                     }
+                    if (++turn == (uint32_t)C::ISSUERS) turn = 0;
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -445,6 +453,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         const float post_scale = p.post_scale;
         const bool dma = lane == 0 && quarter < CHUNKS;                       // this thread drives the TMA traffic of chunk `quarter`
         uint32_t g = 0, tile_par = 0;
+        uint32_t buf = 0, dpar = 0;                                           // partial-sum buffer of K-block g (g % ISSUERS) and its phase
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, tile_par ^= 1) {
             // The tensor pipe is stalled at a tile boundary until this tile's first partial sums are drained, so nothing is
             // computed up front: the tile coordinates are decoded after the first K-block's drain.
@@ -510,9 +519,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             for (int j = 0; j < HALF; ++j) acc[j] = 0.f;
             if (warp == 6 && lane == 0) TL(g, 13);                            // tile prologue (params, residual prefetch) issued
             for (int kb = 0; kb < kblocks; ++kb, ++g) {
-                const uint32_t buf = g & 1;
-                if (p.exp_nolo & 16) mbar_wait<true>(&d_full[buf], (g >> 1) & 1);
-                else mbar_wait(&d_full[buf], (g >> 1) & 1);
+                if (p.exp_nolo & 16) mbar_wait<true>(&d_full[buf], dpar);
+                else mbar_wait(&d_full[buf], dpar);
                 if (warp == 6 && lane == 0) TL(g, 7);
                 tc_fence_after();
                 // software-pipelined drain in 16-column pieces: the load of piece i+1 is in flight while piece i is added;
@@ -542,6 +550,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     }
                 }
                 if (warp == 6 && lane == 0) TL(g, 8);
+                if (++buf == (uint32_t)C::ISSUERS) { buf = 0; dpar ^= 1; }
                 if (kb == 0) after_first_kblock();
             }
             // ---- fused epilogue (pixel per thread == TMEM lane, in place in the slab):
