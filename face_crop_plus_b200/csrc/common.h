@@ -33,6 +33,8 @@ struct Tensor {
 // ----------------------------------------------------------------------------------------------------------
 struct ConvWeights {
     int cout = 0, cin = 0, k = 1;
+    int kh = 0, kw = 0;        // != 0: non-square kernel (tcgen05 kernel only); the stems run as a 7x1 conv over row patches
+    int alg_k = 0;             // != 0: K of the reference convolution this launch implements (FLOP accounting of fcp_profile)
     int cout_pad = 0;          // columns of the packed matrix (multiple of 32)
     float* w_kn = nullptr;     // device [k*k*cin][cout_pad]  (row = (r*k+s)*cin + c), CUDA-core kernel
     float* w_hi = nullptr;     // device [cout_pad][k*k*cin] K-major, tf32-truncated part   (tcgen05 kernel)
@@ -45,6 +47,7 @@ struct ConvOp {
     Tensor in, out;
     const ConvWeights* wt = nullptr;
     int stride = 1, pad = 0;
+    int stride_w = 0, pad_w = -1;   // horizontal stride / padding when they differ from the vertical ones (0 / -1: same)
     int up_in = 0;             // read the input through a nearest x2 upsample (logical size = 2x physical)
     int act = FCP_ACT_NONE;
     float slope = 0.f;
@@ -156,6 +159,10 @@ int launch_stem7(fcp_ctx* ctx, const void* src, int mode, int n, int h, int w, c
 // dev_ptrs[i] = device u8 [hs[i], ws[i], 3]; out = device u8 [n, size_h, size_w, 3]; unscales / paddings are HOST outputs
 int launch_ingest(fcp_ctx* ctx, const uint8_t* const* dev_ptrs, const int32_t* hs, const int32_t* ws, int n, int size_w,
                   int size_h, int border_mode, uint8_t* out, double* unscales, int32_t* paddings);
+// stem, tensor-core route: rows[n][h][wo][32] = for every INPUT row and every output column wo the 7 horizontal taps x 3
+// channels (channel s*3 + c = tap s of conv channel c, 21 used, rest 0; zero outside the image) in fp32, same input
+// conventions as launch_stem7.  The 7x7/s2 conv is then a 7x1 conv with stride (2,1) over `rows` (conv_tc.cu).
+int launch_stem_rows(fcp_ctx* ctx, const void* src, int mode, int n, int h, int w, Tensor rows);
 // conv 3x3/s1 with Cin=3 (RRDB conv_first): f32 NCHW input scaled by in_scale, + bias
 int launch_conv3_first(fcp_ctx* ctx, const float* src_nchw, float in_scale, int n, int h, int w, const float* w_kn,
                        const float* shift, Tensor out);

@@ -58,7 +58,7 @@ struct alignas(64) TcParams {
     CUtensorMap tmBhi, tmBlo;                  // weights [cout_pad][K], K-major
     CUtensorMap tmOut, tmRes;                  // output / residual tensor, box = the tile's 128 pixels x 32 channels
     int out_tma, res_tma;                      // epilogue data paths: bulk tensor store / load usable for this launch
-    int N, Ho, Wo, Cout, Cin, KH, KW, stride, pad;
+    int N, Ho, Wo, Cout, Cin, KH, KW, stride, pad, stride_w, pad_w;   // stride / pad: vertical; *_w: horizontal
     int tiles_x, tiles_y, tiles_n, num_tiles, bw_log2, BH;
     float* out; int out_cs, out_co;
     const float* scale; const float* shift;
@@ -318,11 +318,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 const int ho0 = (rem / p.tiles_x) * p.BH, wo0 = (rem % p.tiles_x) * BW;
                 int tap = 0, cc = 0, r = 0, sx = 0;                          // K-block = (tap (r, sx), 32-channel chunk cc)
                 for (int kb = 0; kb < kblocks; ++kb) {
-                    int dy = r - p.pad, dx = sx - p.pad, map = 0;
+                    int dy = r - p.pad, dx = sx - p.pad_w, map = 0;
                     if (p.stride == 2) {   // input row 2*ho + dy lives in parity view (dy & 1) at row ho + (dy - (dy & 1)) / 2
-                        const int py = dy & 1, px = dx & 1;
-                        map = py * 2 + px;
+                        const int py = dy & 1;
+                        map = py * 2;
                         dy = (dy - py) >> 1;
+                    }
+                    if (p.stride_w == 2) {
+                        const int px = dx & 1;
+                        map += px;
                         dx = (dx - px) >> 1;
                     }
                     const int c0 = cc * KB, kcol = tap * p.Cin + c0;
@@ -693,8 +697,9 @@ int launch(fcp_ctx* ctx, const TcParams& p) {
 bool conv_tc_supported(const ConvOp& op) {
     const ConvWeights& wt = *op.wt;
     if (wt.cin % KB != 0 || op.up_in) return false;
-    if (op.stride != 1 && op.stride != 2) return false;
-    if (op.stride == 2 && !(wt.k == 1 || wt.k == 3)) return false;
+    const int stride_w = op.stride_w ? op.stride_w : op.stride;
+    if ((op.stride != 1 && op.stride != 2) || (stride_w != 1 && stride_w != 2)) return false;
+    if (op.stride == 2 && !(wt.k == 1 || wt.k == 3 || wt.kh)) return false;
     if ((op.in.cs | op.in.co) & 3) return false;
     if ((size_t)op.out.h * op.out.w < 64) return false;       // pooled 1x1 maps etc. stay on the CUDA-core kernel
     if (op.res1 && op.res2) return false;                     // the epilogue prefetches one residual source (no graph uses both)
@@ -711,8 +716,10 @@ int launch_conv_tc(fcp_ctx* ctx, const ConvOp& op) {
     TcParams p{};
     const int H = op.in.h, W = op.in.w, cs = op.in.cs;
     p.N = op.in.n; p.Ho = op.out.h; p.Wo = op.out.w; p.Cout = wt.cout; p.Cin = wt.cin;
-    p.KH = p.KW = wt.k; p.stride = op.stride; p.pad = op.pad;
-    if ((H + 2 * op.pad - wt.k) / op.stride + 1 != p.Ho || (W + 2 * op.pad - wt.k) / op.stride + 1 != p.Wo)
+    p.KH = wt.kh ? wt.kh : wt.k; p.KW = wt.kw ? wt.kw : wt.k;
+    p.stride = op.stride; p.pad = op.pad;
+    p.stride_w = op.stride_w ? op.stride_w : op.stride; p.pad_w = op.pad_w >= 0 ? op.pad_w : op.pad;
+    if ((H + 2 * p.pad - p.KH) / p.stride + 1 != p.Ho || (W + 2 * p.pad_w - p.KW) / p.stride_w + 1 != p.Wo)
         return fail(ctx, FCP_ERR_INVALID, "conv: output shape mismatch");
     // spatial box of 128 output pixels: widest power-of-two width that does not overshoot the row by more than 2x
     int bw_log2 = 7;
@@ -733,17 +740,17 @@ int launch_conv_tc(fcp_ctx* ctx, const ConvOp& op) {
     p.num_tiles = p.N * p.tiles_x * p.tiles_y * p.tiles_n;
     // ---- tensor maps
     float* base = op.in.p + op.in.co;
-    const int nviews = op.stride == 2 ? 4 : 1;
-    for (int v = 0; v < nviews; ++v) {
-        const int py = v >> 1, px = v & 1, st = op.stride;
-        cuuint64_t dims[4] = {(cuuint64_t)wt.cin, (cuuint64_t)((W - px + st - 1) / st), (cuuint64_t)((H - py + st - 1) / st), (cuuint64_t)p.N};
-        cuuint64_t strides[3] = {(cuuint64_t)st * cs * 4, (cuuint64_t)st * W * cs * 4, (cuuint64_t)H * W * cs * 4};
-        cuuint32_t box[4] = {KB, (cuuint32_t)BW, (cuuint32_t)BH, 1};
-        if (dims[1] == 0 || dims[2] == 0) { dims[1] = dims[1] ? dims[1] : 1; dims[2] = dims[2] ? dims[2] : 1; }
-        if (!make_map(&p.tmA[v], base + ((size_t)py * W + px) * cs, 4, dims, strides, box))
-            return fail(ctx, FCP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the activation tensor");
-    }
-    const cuuint64_t K = (cuuint64_t)wt.k * wt.k * wt.cin;
+    for (int py = 0; py < p.stride; ++py)
+        for (int px = 0; px < p.stride_w; ++px) {
+            const int sh = p.stride, sw = p.stride_w;
+            cuuint64_t dims[4] = {(cuuint64_t)wt.cin, (cuuint64_t)((W - px + sw - 1) / sw), (cuuint64_t)((H - py + sh - 1) / sh), (cuuint64_t)p.N};
+            cuuint64_t strides[3] = {(cuuint64_t)sw * cs * 4, (cuuint64_t)sh * W * cs * 4, (cuuint64_t)H * W * cs * 4};
+            cuuint32_t box[4] = {KB, (cuuint32_t)BW, (cuuint32_t)BH, 1};
+            if (dims[1] == 0 || dims[2] == 0) { dims[1] = dims[1] ? dims[1] : 1; dims[2] = dims[2] ? dims[2] : 1; }
+            if (!make_map(&p.tmA[py * 2 + px], base + ((size_t)py * W + px) * cs, 4, dims, strides, box))
+                return fail(ctx, FCP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the activation tensor");
+        }
+    const cuuint64_t K = (cuuint64_t)p.KH * p.KW * wt.cin;
     cuuint64_t bdims[2] = {K, (cuuint64_t)wt.cout_pad};
     cuuint64_t bstr[1] = {K * 4};
     cuuint32_t bbox[2] = {KB, (cuuint32_t)BN};

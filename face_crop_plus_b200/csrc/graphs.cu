@@ -68,6 +68,25 @@ bool Exec::conv(const std::string& name, Tensor in, Tensor out, int stride, int 
     return ok();
 }
 
+// 7x7/s2 stem + folded BN + ReLU (`body.conv1`, `cp.resnet.conv1`).  Tensor-core route: one HBM-bound kernel gathers, for
+// every input row, the 7 horizontal taps x 3 channels of each output column into a 32-channel fp32 tensor; the conv is
+// then a 7x1 / stride (2,1) conv over it on the tcgen05 kernel (7 K-blocks; vertical padding = TMA zero fill).
+// FCP_CONV_IMPL=0 keeps the CUDA-core stem kernel.
+static void stem7(Exec& ex, const std::string& name, const void* src, int mode, int nb, int h, int w, Tensor out) {
+    const ConvWeights* stem = ex.W(name);
+    if (!stem || !ex.ok()) return;
+    if (!ex.ctx->use_tc || getenv("FCP_STEM_FFMA")) {
+        if (!ex.dry) ex.status = launch_stem7(ex.ctx, src, mode, nb, h, w, stem->w_kn, stem->scale, stem->shift, out);
+        return;
+    }
+    Tensor rows = ex.alloc(nb, h, out.w, 32);
+    if (ex.ok() && !ex.dry) ex.status = launch_stem_rows(ex.ctx, src, mode, nb, h, w, rows);
+    ConvOp e;
+    e.stride_w = 1; e.pad_w = 0;
+    ex.conv(name + ".rows", rows, out, 2, 3, FCP_ACT_RELU, e);
+    ex.free(rows);
+}
+
 static ConvOp with_res1(Tensor r) {
     ConvOp e;
     e.res1 = r.p; e.res1_cs = r.cs; e.res1_co = r.co;
@@ -78,6 +97,7 @@ static ConvOp with_res1(Tensor r) {
 int finalize_retinaface(fcp_ctx* ctx) {
     Model& m = ctx->models[FCP_MODEL_RETINAFACE];
     FCP_TRY(pack_conv(ctx, m, {"body.conv1"}, "body.bn1", "body.conv1"));
+    FCP_TRY(pack_stem_rows(ctx, m, "body.conv1", "body.conv1.rows"));
     const int blocks[4] = {3, 4, 6, 3};
     for (int li = 1; li <= 4; ++li)
         for (int b = 0; b < blocks[li - 1]; ++b) {
@@ -142,7 +162,7 @@ static int retinaface_forward(Exec& ex, const uint8_t* images, int nb, int h, in
     const ConvWeights* stem = ex.W("body.conv1");
     if (!stem) return ex.status;
     Tensor s1 = ex.alloc(nb, odim(h, 7, 2, 3), odim(w, 7, 2, 3), 64);
-    if (ex.ok() && !ex.dry) ex.status = launch_stem7(ex.ctx, images, 0, nb, h, w, stem->w_kn, stem->scale, stem->shift, s1);
+    stem7(ex, "body.conv1", images, 0, nb, h, w, s1);
     Tensor x = ex.alloc(nb, odim(s1.h, 3, 2, 1), odim(s1.w, 3, 2, 1), 64);
     if (ex.ok() && !ex.dry) ex.status = launch_maxpool3s2(ex.ctx, s1, x);
     ex.free(s1);
@@ -198,6 +218,7 @@ static int retinaface_forward(Exec& ex, const uint8_t* images, int nb, int h, in
 int finalize_bisenet(fcp_ctx* ctx) {
     Model& m = ctx->models[FCP_MODEL_BISENET];
     FCP_TRY(pack_conv(ctx, m, {"cp.resnet.conv1"}, "cp.resnet.bn1", "cp.resnet.conv1"));
+    FCP_TRY(pack_stem_rows(ctx, m, "cp.resnet.conv1", "cp.resnet.conv1.rows"));
     for (int li = 1; li <= 4; ++li)
         for (int b = 0; b < 2; ++b) {
             std::string p = "cp.resnet.layer" + std::to_string(li) + "." + std::to_string(b);
@@ -256,7 +277,7 @@ static int bisenet_forward(Exec& ex, const float* in3, int nb, Tensor& logits) {
     const ConvWeights* stem = ex.W("cp.resnet.conv1");
     if (!stem) return ex.status;
     Tensor s1 = ex.alloc(nb, 256, 256, 64);
-    if (ex.ok() && !ex.dry) ex.status = launch_stem7(ex.ctx, in3, 1, nb, 512, 512, stem->w_kn, stem->scale, stem->shift, s1);
+    stem7(ex, "cp.resnet.conv1", in3, 1, nb, 512, 512, s1);
     Tensor x = ex.alloc(nb, 128, 128, 64);
     if (ex.ok() && !ex.dry) ex.status = launch_maxpool3s2(ex.ctx, s1, x);
     ex.free(s1);

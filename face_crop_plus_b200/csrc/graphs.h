@@ -8,6 +8,10 @@ bool is_device_ptr(const void* p);
 int pack_conv(fcp_ctx* ctx, Model& m, const std::vector<std::string>& convs, const std::string& bn,
               const std::string& name);
 
+// tensor-core packing of a 7x7 stem (`conv` = name of the already packed square conv, whose folded BN it shares):
+// weights [64][7 vertical taps][32 = 7 horizontal taps x 3 channels, zero padded], registered as `name`
+int pack_stem_rows(fcp_ctx* ctx, Model& m, const std::string& conv, const std::string& name);
+
 // borrowed input: used in place when it already lives on the device, otherwise copied H2D on the context stream
 class DevIn {
 public:

@@ -314,6 +314,47 @@ int launch_stem7(fcp_ctx* ctx, const void* src, int mode, int n, int h, int w, c
     return FCP_OK;
 }
 
+// rows[n][hi][wo][32]: channel s*3 + c = input(hi, 2*wo + s - 3, conv channel c), 0 outside the image / for channels >= 21.
+// One thread per (hi, wo): 128 contiguous output bytes; neighbouring threads re-read overlapping inputs through L1.
+template <int MODE>
+__global__ void stem_rows_kernel(const void* __restrict__ src, int N, int H, int W, int Wo, float* __restrict__ rows, int cs) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)N * H * Wo;
+    if (idx >= total) return;
+    const int wo = (int)(idx % Wo);
+    const size_t t = idx / Wo;                          // n * H + hi
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+#pragma unroll
+    for (int sx = 0; sx < 7; ++sx) {
+        const int wi = 2 * wo + sx - 3;
+        if (wi < 0 || wi >= W) continue;
+        if (MODE == 0) {                                // RGB uint8 -> BGR, minus (104,117,123): retinaface.py:450-451
+            const uint8_t* px = static_cast<const uint8_t*>(src) + (t * W + wi) * 3;
+            v[sx * 3 + 0] = (float)px[2] - 104.f;
+            v[sx * 3 + 1] = (float)px[1] - 117.f;
+            v[sx * 3 + 2] = (float)px[0] - 123.f;
+        } else {
+            const float* px = static_cast<const float*>(src) + (t * W + wi) * 3;
+            v[sx * 3 + 0] = px[0]; v[sx * 3 + 1] = px[1]; v[sx * 3 + 2] = px[2];
+        }
+    }
+    float4* dst = reinterpret_cast<float4*>(rows + idx * cs);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+
+int launch_stem_rows(fcp_ctx* ctx, const void* src, int mode, int n, int h, int w, Tensor rows) {
+    if (rows.c != 32 || rows.co != 0 || rows.cs % 4 != 0 || rows.h != h) return fail(ctx, FCP_ERR_INVALID, "stem rows: bad tensor");
+    const size_t total = (size_t)n * h * rows.w;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (mode == 0) stem_rows_kernel<0><<<blocks, 256, 0, ctx->stream>>>(src, n, h, w, rows.w, rows.p, rows.cs);
+    else stem_rows_kernel<1><<<blocks, 256, 0, ctx->stream>>>(src, n, h, w, rows.w, rows.p, rows.cs);
+    FCP_KERNEL_CHECK(ctx);
+    return FCP_OK;
+}
+
 int launch_conv3_first(fcp_ctx* ctx, const float* src_nchw, float in_div, int n, int h, int w, const float* w_kn,
                        const float* shift, Tensor out) {
     size_t total = (size_t)n * h * w;

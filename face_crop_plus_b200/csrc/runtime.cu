@@ -169,6 +169,32 @@ int pack_conv(fcp_ctx* ctx, Model& m, const std::vector<std::string>& convs, con
     return FCP_OK;
 }
 
+int pack_stem_rows(fcp_ctx* ctx, Model& m, const std::string& conv, const std::string& name) {
+    const HostTensor* w = find(m, conv + ".weight");
+    auto it = m.conv.find(conv);
+    if (!w || w->shape.size() != 4 || w->shape[1] != 3 || w->shape[2] != 7 || w->shape[3] != 7 || it == m.conv.end())
+        return fail(ctx, FCP_ERR_STATE, "stem weights missing or not 7x7x3: " + conv);
+    ConvWeights cw = it->second;                       // shares scale / shift (folded BN) with the square packing
+    cw.cin = 32; cw.k = 7; cw.kh = 7; cw.kw = 1; cw.alg_k = 147;
+    cw.w_kn = nullptr;                                 // no CUDA-core packing: this route exists on the tensor cores only
+    const int K = 7 * 32;
+    std::vector<float> whi((size_t)cw.cout_pad * K, 0.f), wlo((size_t)cw.cout_pad * K, 0.f);
+    for (int o = 0; o < cw.cout; ++o)
+        for (int c = 0; c < 3; ++c)
+            for (int r = 0; r < 7; ++r)
+                for (int sx = 0; sx < 7; ++sx) {
+                    const float v = w->data[(((size_t)o * 3 + c) * 7 + r) * 7 + sx];
+                    const size_t kk = (size_t)r * 32 + sx * 3 + c;
+                    const float hi = tf32_trunc(v);
+                    whi[(size_t)o * K + kk] = hi;
+                    wlo[(size_t)o * K + kk] = tf32_trunc(v - hi);
+                }
+    FCP_TRY(upload(ctx, whi, &cw.w_hi));
+    FCP_TRY(upload(ctx, wlo, &cw.w_lo));
+    m.conv[name] = cw;
+    return FCP_OK;
+}
+
 // ------------------------------------------------------------------------------------- host/device staging
 bool is_device_ptr(const void* p) {
     if (!p) return false;
@@ -215,6 +241,7 @@ DevOut::~DevOut() {
 
 int run_conv(fcp_ctx* ctx, const ConvOp& op) {
     const bool tc = op.impl == 1 && conv_tc_supported(op);   // shapes the tensor-core kernel does not cover use the CUDA-core kernel
+    if (!tc && !op.wt->w_kn) return fail(ctx, FCP_ERR_INVALID, "conv: this packing exists for the tensor-core kernel only");
     if (!ctx->profile) return tc ? launch_conv_tc(ctx, op) : launch_conv_ffma(ctx, op);
     if (ctx->prof_used + 2 > ctx->prof_events.size()) {
         cudaEvent_t a, b;
@@ -229,10 +256,10 @@ int run_conv(fcp_ctx* ctx, const ConvOp& op) {
     int s = tc ? launch_conv_tc(ctx, op) : launch_conv_ffma(ctx, op);
     FCP_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
     const ConvWeights& w = *op.wt;
-    const double M = (double)op.out.n * op.out.h * op.out.w, K = (double)w.k * w.k * w.cin;
+    const double M = (double)op.out.n * op.out.h * op.out.w, K = w.alg_k ? (double)w.alg_k : (double)w.k * w.k * w.cin;
     ctx->prof_flops += 2.0 * M * w.cout * K;
     ctx->prof_bytes += 4.0 * ((double)op.in.pixels() * w.cin + M * w.cout + K * w.cout);
-    ctx->prof_recs.push_back({(int)M, w.cout, w.cin, w.k, op.stride, tc ? 1 : 0});
+    ctx->prof_recs.push_back({(int)M, w.cout, w.alg_k ? 3 : w.cin, w.k, op.stride, tc ? 1 : 0});   // stems: the reference's 7x7x3
     return s;
 }
 
