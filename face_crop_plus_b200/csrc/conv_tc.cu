@@ -581,20 +581,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                         return x;
                     }
                 };
+                // software-pipelined by hand (the shared-memory accesses are volatile asm, the compiler keeps their order):
+                // the six loads of step i+1 are issued before the arithmetic of step i
+                struct Step { float4 sc0, sc1, sh0, sh1, r0, r1; };
+                auto load_step = [&](int j) -> Step {
+                    Step t;
+                    t.sc0 = lds_f4(par + 4 * j); t.sc1 = lds_f4(par + 4 * j + 16);
+                    t.sh0 = lds_f4(par + 4 * (HALF + j)); t.sh1 = lds_f4(par + 4 * (HALF + j) + 16);
+                    t.r0 = make_float4(0.f, 0.f, 0.f, 0.f); t.r1 = t.r0;
+                    if (has_res) {
+                        t.r0 = lds_f4(slab_addr(j >> 5, lane, (j >> 2) & 7));
+                        t.r1 = lds_f4(slab_addr(j >> 5, lane, ((j >> 2) & 7) + 1));
+                    }
+                    return t;
+                };
+                Step cur = load_step(0);
 #pragma unroll
                 for (int j = 0; j < HALF; j += 8) {
                     const uint32_t a0 = slab_addr(j >> 5, lane, (j >> 2) & 7), a1 = slab_addr(j >> 5, lane, ((j >> 2) & 7) + 1);
-                    const float4 sc0 = lds_f4(par + 4 * j), sc1 = lds_f4(par + 4 * j + 16);
-                    const float4 sh0 = lds_f4(par + 4 * (HALF + j)), sh1 = lds_f4(par + 4 * (HALF + j) + 16);
-                    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
-                    if (has_res) { r0 = lds_f4(a0); r1 = lds_f4(a1); }
+                    Step nxt = cur;
+                    if (j + 8 < HALF) nxt = load_step(j + 8);
                     float4 x0, x1;
-                    x0.x = fuse(acc[j], sc0.x, sh0.x, r0.x); x0.y = fuse(acc[j + 1], sc0.y, sh0.y, r0.y);
-                    x0.z = fuse(acc[j + 2], sc0.z, sh0.z, r0.z); x0.w = fuse(acc[j + 3], sc0.w, sh0.w, r0.w);
-                    x1.x = fuse(acc[j + 4], sc1.x, sh1.x, r1.x); x1.y = fuse(acc[j + 5], sc1.y, sh1.y, r1.y);
-                    x1.z = fuse(acc[j + 6], sc1.z, sh1.z, r1.z); x1.w = fuse(acc[j + 7], sc1.w, sh1.w, r1.w);
+                    x0.x = fuse(acc[j], cur.sc0.x, cur.sh0.x, cur.r0.x); x0.y = fuse(acc[j + 1], cur.sc0.y, cur.sh0.y, cur.r0.y);
+                    x0.z = fuse(acc[j + 2], cur.sc0.z, cur.sh0.z, cur.r0.z); x0.w = fuse(acc[j + 3], cur.sc0.w, cur.sh0.w, cur.r0.w);
+                    x1.x = fuse(acc[j + 4], cur.sc1.x, cur.sh1.x, cur.r1.x); x1.y = fuse(acc[j + 5], cur.sc1.y, cur.sh1.y, cur.r1.y);
+                    x1.z = fuse(acc[j + 6], cur.sc1.z, cur.sh1.z, cur.r1.z); x1.w = fuse(acc[j + 7], cur.sc1.w, cur.sh1.w, cur.r1.w);
                     sts_f4(a0, x0);
                     sts_f4(a1, x1);
+                    cur = nxt;
                 }
             };
             if (post_scale == 1.f && !r_post && (neg_slope == 0.f || neg_slope == 1.f)) phase1(std::true_type{});
