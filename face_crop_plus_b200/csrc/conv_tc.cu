@@ -27,7 +27,7 @@
 // CTA = 15 warps, persistent over output tiles (128 pixels x BN channels):
 //   warp 0      TMA producer          full_a[l] <- A bytes (waits a_free[l]);  full_b[s] <- weight bytes (waits empty[s])
 //   warps 2-5   hi/lo converters      a_free[l], conv[s] <- 4 arrivals (1/warp) (wait full_a[l], then empty[s] for the TMEM slot)
-//   warps 1,14,(15: BN=64)  MMA issuers (1 lane each, K-blocks round-robin, one partial-sum buffer each)  empty[s], d_full[b] <- tcgen05.commit (wait conv[s], full_b[s], d_empty[b])
+//   warps 1,14,(15: BN<=64)  MMA issuers (1 lane each, K-blocks round-robin, one partial-sum buffer each)  empty[s], d_full[b] <- tcgen05.commit (wait conv[s], full_b[s], d_empty[b])
 //   warps 6-13  accumulate+epilogue   d_empty[b] <- 8 arrivals (1/warp) (wait d_full[b]); per K-block TMEM -> regs (+=),
 //               after the last K-block: fused epilogue -> HBM.  Warp w owns TMEM lanes 32*(w%4).. and half of the columns.
 // Two TMEM partial-sum buffers let the drain of K-block i overlap the MMAs of K-block i+1.
@@ -46,7 +46,7 @@ namespace {
 constexpr int TILE_M = 128;
 constexpr int KB = 32;                         // channels per K-block (128 bytes of fp32)
 constexpr int A_TILE_BYTES = TILE_M * KB * 4;  // 16 KiB
-// MMA-issuing warps: warp 1, warp 14 and (BN = 64 only) warp 15, one lane each, K-blocks round-robin.  Invariant: there
+// MMA-issuing warps: warp 1, warp 14 and (BN <= 64 only) warp 15, one lane each, K-blocks round-robin.  Invariant: there
 // are exactly as many partial-sum buffers in tensor memory as issuers and issuer i only ever writes buffer i, so a parity
 // wait on d_empty can never be more than one phase ahead (3 issuers sharing 2 buffers touch a buffer out of order and
 // the mbarrier parity waits alias -> corrupted sums and a deadlock; measured the hard way).
@@ -243,11 +243,11 @@ template <int BN> struct Cfg {
     // retire ~ 3300 cycles, measured) divided by its depth, not by any bandwidth.  The fp32 A tile only lives from its
     // landing to its conversion, so it gets its own short ring (LANDINGS); a pipeline STAGE is a weight slot in shared
     // memory plus an (a_hi | a_lo) slot in tensor memory, both held until the K-block's MMAs retire.
-    static constexpr int STAGES = BN >= 128 ? 4 : (BN == 64 ? 5 : 7);
+    static constexpr int STAGES = BN >= 128 ? 4 : (BN == 64 ? 5 : 6);
     static constexpr int LANDINGS = BN >= 128 ? 2 : 3;
     // One tcgen05.mma costs its issuing thread ~85 cycles whatever N is, so the narrow BN = 64 tiles (32-cycle MMAs) are
-    // issue-bound: they get a third issuer + accumulator and one stage less (tensor memory is 512 columns).
-    static constexpr int ISSUERS = BN == 64 ? 3 : 2;
+    // issue-bound: BN <= 64 gets a third issuer + accumulator and one stage less (tensor memory is 512 columns).
+    static constexpr int ISSUERS = BN <= 64 ? 3 : 2;
     // tensor memory: [0, ISSUERS*BN) partial-sum buffers; then STAGES x (a_hi 32 cols | a_lo 32 cols)
     static constexpr int TMEM_A0 = ISSUERS * BN;
     static constexpr int TMEM_COLS = 512;
