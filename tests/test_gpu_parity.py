@@ -60,6 +60,9 @@ CONV_CASES = [  # (n, h, w, cin, cout, k, stride, pad, act, residual)
     (1, 64, 64, 256, 19, 1, 1, 0, "none", False),
     (3, 9, 9, 32, 32, 1, 1, 0, "sigmoid", False),
     (1, 40, 40, 192, 64, 3, 1, 1, "none", False),
+    (4, 64, 64, 64, 256, 1, 1, 0, "relu", True),      # 256 tiles > 148 CTAs: slab / residual reuse across a CTA's tiles
+    (2, 30, 50, 64, 48, 3, 1, 1, "relu", True),       # Cout = 32 + 16: second TMA chunk clipped, residual zero-filled
+    (1, 96, 96, 32, 160, 3, 2, 1, "lrelu", False),    # general epilogue form, stride-2 parity views, cout_pad 160 -> BN 32
 ]
 
 
