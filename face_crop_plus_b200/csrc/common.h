@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -118,6 +119,11 @@ struct fcp_ctx {
     double prof_flops = 0, prof_bytes = 0;
     struct ProfRec { int m, cout, cin, k, stride, tc; };
     std::vector<ProfRec> prof_recs;     // one per event pair (FCP_TRACE=1 prints a per-shape table)
+    // fcp_pipeline with HOST images: the batch is copied H2D per detector micro-batch on a second stream, one micro-batch
+    // ahead of the compute stream (the hook runs at the top of every detector micro-batch)
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> copy_events;
+    std::function<int(int)> on_microbatch;
 };
 
 namespace fcp {

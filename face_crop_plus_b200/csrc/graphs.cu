@@ -468,6 +468,7 @@ static int detect_core(fcp_ctx* ctx, const uint8_t* images, int n, int h, int w,
     int status = FCP_OK;
     for (int b0 = 0; b0 < n && status == FCP_OK; b0 += mb) {
         int nb = std::min(mb, n - b0);
+        if (ctx->on_microbatch && (status = ctx->on_microbatch(b0)) != FCP_OK) break;
         ctx->arena.reset();
         Exec ex{ctx, model, false};
         Tensor lvl[3];
@@ -864,17 +865,52 @@ int fcp_pipeline(fcp_ctx* ctx, const uint8_t* images, int n, int h, int w, const
     if (!images || n < 1 || max_faces < 1 || !out_count || !target || !out_crops || strategy < 0 || strategy > 2 ||
         border_mode < 0 || border_mode > 4)
         return fail(ctx, FCP_ERR_INVALID, "fcp_pipeline: bad argument");
-    DevIn img, pad, tgt;
-    FCP_TRY(img.init(ctx, images, (size_t)n * h * w * 3));
+    DevIn pad, tgt;
     FCP_TRY(pad.init(ctx, paddings, sizeof(int32_t) * 4 * n));
     FCP_TRY(tgt.init(ctx, target, sizeof(float) * 10));
+    // Images in host memory are copied per detector micro-batch on a second stream, one micro-batch ahead of the compute
+    // stream, so that (with pinned buffers) only the first micro-batch's copy is exposed.
+    const uint8_t* dimg = images;
+    uint8_t* staged = nullptr;
+    const size_t img_bytes = (size_t)h * w * 3;
+    if (!is_device_ptr(images)) {
+        const int mb = std::min(ctx->det_mb, n), chunks = (n + mb - 1) / mb;
+        FCP_CUDA(ctx, cudaMallocAsync(&staged, img_bytes * n, ctx->stream));
+        if (!ctx->copy_stream) FCP_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        while ((int)ctx->copy_events.size() < chunks + 1) {
+            cudaEvent_t e;
+            FCP_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->copy_events.push_back(e);
+        }
+        FCP_CUDA(ctx, cudaEventRecord(ctx->copy_events[chunks], ctx->stream));              // the allocation is stream-ordered
+        FCP_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_events[chunks], 0));
+        auto issue = [ctx, images, staged, img_bytes, mb, n, chunks](int c) -> int {
+            if (c >= chunks) return FCP_OK;
+            const size_t off = (size_t)c * mb * img_bytes, bytes = (size_t)std::min(mb, n - c * mb) * img_bytes;
+            FCP_CUDA(ctx, cudaMemcpyAsync(staged + off, images + off, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+            FCP_CUDA(ctx, cudaEventRecord(ctx->copy_events[c], ctx->copy_stream));
+            return FCP_OK;
+        };
+        FCP_TRY(issue(0));
+        ctx->on_microbatch = [ctx, issue, mb](int b0) -> int {
+            const int c = b0 / mb;
+            FCP_TRY(issue(c + 1));
+            FCP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_events[c], 0));
+            return FCP_OK;
+        };
+        dimg = staged;
+    }
     float* faces; int32_t* face_img; int32_t* face_count;
     FCP_CUDA(ctx, cudaMallocAsync(&faces, sizeof(float) * 16 * max_faces, ctx->stream));
     FCP_CUDA(ctx, cudaMallocAsync(&face_img, sizeof(int32_t) * max_faces, ctx->stream));
     FCP_CUDA(ctx, cudaMallocAsync(&face_count, sizeof(int32_t), ctx->stream));
-    auto cleanup = [&]() { cudaFreeAsync(faces, ctx->stream); cudaFreeAsync(face_img, ctx->stream); cudaFreeAsync(face_count, ctx->stream); };
-    int s = detect_core(ctx, img.as<uint8_t>(), n, h, w, vis_threshold, nms_threshold, strategy, max_faces, faces, face_img,
+    auto cleanup = [&]() {
+        cudaFreeAsync(faces, ctx->stream); cudaFreeAsync(face_img, ctx->stream); cudaFreeAsync(face_count, ctx->stream);
+        if (staged) { cudaStreamSynchronize(ctx->copy_stream); cudaFreeAsync(staged, ctx->stream); }   // no copy may outlive the buffer
+    };
+    int s = detect_core(ctx, dimg, n, h, w, vis_threshold, nms_threshold, strategy, max_faces, faces, face_img,
                         face_count, nullptr);
+    ctx->on_microbatch = nullptr;
     if (s != FCP_OK) { cleanup(); return s; }
     // landmark un-pad (cropper.py:822) happens while unpacking the face records
     DevOut lms, crops, mats, valid, lab, hist;
@@ -891,7 +927,7 @@ int fcp_pipeline(fcp_ctx* ctx, const uint8_t* images, int n, int h, int w, const
         if (s == FCP_OK) s = mats.init(ctx, out_matrices, sizeof(double) * 6 * f, true);
         if (s == FCP_OK) s = valid.init(ctx, out_valid, f, true);
         if (s == FCP_OK)
-            s = align_core(ctx, img.as<uint8_t>(), n, h, w, nullptr, nullptr, nullptr, pad.as<int32_t>(), face_img, nullptr,
+            s = align_core(ctx, dimg, n, h, w, nullptr, nullptr, nullptr, pad.as<int32_t>(), face_img, nullptr,
                            lms.as<float>(), f, tgt.as<float>(), out_w, out_h, border_mode, allow_skew, crops.as<uint8_t>(),
                            mats.as<double>(), valid.as<uint8_t>());
         if (s == FCP_OK && do_parse) {

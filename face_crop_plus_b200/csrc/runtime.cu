@@ -303,6 +303,8 @@ void fcp_destroy(fcp_ctx* ctx) {
     cudaDeviceSynchronize();
     for (void* p : ctx->device_allocs) cudaFree(p);
     for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->copy_events) cudaEventDestroy(e);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
