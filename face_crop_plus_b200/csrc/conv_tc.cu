@@ -258,7 +258,7 @@ template <int BN> struct Cfg {
     static constexpr int CHUNKS = HALF / 32;                              // 32-channel (128-byte) chunks per group
     static constexpr int CHUNK_BYTES = TILE_M * 128;                      // one chunk = the tile's 128 pixels x 32 channels
     static constexpr int S_BYTES = GROUPS * CHUNKS * CHUNK_BYTES;
-    static constexpr int PAR_BYTES = GROUPS * 2 * HALF * 4;               // per group: scale[HALF] | shift[HALF]
+    static constexpr int PAR_BYTES = GROUPS * 2 * HALF * 4;               // per group: shift[HALF] (+ spare)
     static constexpr int PIPE_BYTES = STAGES * B_SLOT_BYTES + LANDINGS * A_TILE_BYTES;
     static constexpr int SMEM_BYTES = PIPE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/ + S_BYTES + PAR_BYTES;
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
@@ -467,10 +467,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 const int ho = ho0 + (prow >> p.bw_log2), wo = wo0 + (prow & (BW - 1));
                 return (ho < p.Ho && wo < p.Wo) ? (img * p.Ho + ho) * p.Wo + wo : -1;
             };
-            // ---- after the first K-block: decode the tile; fetch the group's folded-BN scale/shift (arrays are padded to
-            //      cout_pad >= n0 + HALF) asynchronously - every warp of the group issues the same 16-byte copies (lanes
-            //      [0, HALF/4): scale, [16, 16 + HALF/4): shift) and later waits for its own, so no barrier has to publish
-            //      them; safe to overwrite: every warp has passed the pre-store barrier of the previous tile.  Then: the
+            // ---- after the first K-block: decode the tile; fetch the group's folded-BN shift (the scale is folded into the
+            //      weights; arrays are padded to cout_pad >= n0 + HALF) asynchronously - every warp of the group issues the
+            //      same 16-byte copies (lanes [0, HALF/4)) and later waits for its own, so no barrier has to publish them;
+            //      safe to overwrite: every warp has passed the pre-store barrier of the previous tile.  Then: the
             //      previous tile's bulk stores have released the slab (waited for by the threads that issued them, published
             //      by one group barrier), and the residual chunks (128 pixels x 32 channels each) stream into the slab while
             //      the K loop runs.
@@ -480,13 +480,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 const int rem = m_tile - img * tiles_per_img;
                 ho0 = (rem / p.tiles_x) * p.BH; wo0 = (rem % p.tiles_x) * BW;
                 n0 = n_tile * BN + half * HALF;                               // first channel of this group
-                {
-                    const int piece = lane & 15;
-                    if (piece < HALF / 4) {
-                        const float* src = (lane < 16 ? p.scale : p.shift) + n0 + piece * 4;
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(par + (lane < 16 ? 0 : 4 * HALF) + piece * 16), "l"(src) : "memory");
-                    }
-                }
+                if (lane < HALF / 4)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(par + lane * 16), "l"(p.shift + n0 + lane * 4) : "memory");
                 if (dma) bulk_wait_read();
                 group_sync();
                 if (!has_res) return;
@@ -521,6 +516,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             float acc[HALF];
 #pragma unroll
             for (int j = 0; j < HALF; ++j) acc[j] = 0.f;
+            // acc += shift (per channel; the weights carry the folded-BN scale): needs the params fetched after the first
+            // K-block, so it rides on the second K-block's drain
+            auto add_shift = [&]() {
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < HALF; j += 4) {
+                    const float4 sh = lds_f4(par + 4 * j);
+                    acc[j] += sh.x; acc[j + 1] += sh.y; acc[j + 2] += sh.z; acc[j + 3] += sh.w;
+                }
+            };
             if (warp == 6 && lane == 0) TL(g, 13);                            // tile prologue (params, residual prefetch) issued
             for (int kb = 0; kb < kblocks; ++kb, ++g) {
                 if (p.exp_nolo & 16) mbar_wait<true>(&d_full[buf], dpar);
@@ -556,9 +562,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 if (warp == 6 && lane == 0) TL(g, 8);
                 if (++buf == (uint32_t)C::ISSUERS) { buf = 0; dpar ^= 1; }
                 if (kb == 0) after_first_kblock();
+                else if (kb == 1) add_shift();                                // off the tile-boundary critical path
             }
+            if (kblocks == 1) add_shift();
             // ---- fused epilogue (pixel per thread == TMEM lane, in place in the slab):
-            //      y = post_scale * act(acc * scale + shift [+ res1]) [+ res2]
+            //      y = post_scale * act(acc [+ res1]) [+ res2]      (acc already = conv*scale + shift)
             asm volatile("cp.async.wait_all;" ::: "memory");                  // params (+ this warp's rows of a cp.async residual)
             if (has_res && p.res_tma) mbar_wait(rbar, tile_par);
             __syncwarp();
@@ -569,8 +577,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             auto phase1 = [&](auto simple_tag) {
                 constexpr bool SIMPLE = decltype(simple_tag)::value;
                 const float lo_clamp = neg_slope == 0.f ? 0.f : -INFINITY;    // relu | none
-                auto fuse = [&](const float a, const float sc, const float sh, const float rv) -> float {
-                    float x = a * sc + sh;
+                auto fuse = [&](float x, const float rv) -> float {           // x = conv*scale + shift already
                     if constexpr (SIMPLE) {
                         if (has_res) x += rv;
                         return fmaxf(x, lo_clamp);
@@ -582,12 +589,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     }
                 };
                 // software-pipelined by hand (the shared-memory accesses are volatile asm, the compiler keeps their order):
-                // the six loads of step i+1 are issued before the arithmetic of step i
-                struct Step { float4 sc0, sc1, sh0, sh1, r0, r1; };
+                // the residual loads of step i+1 are issued before the arithmetic of step i
+                struct Step { float4 r0, r1; };
                 auto load_step = [&](int j) -> Step {
                     Step t;
-                    t.sc0 = lds_f4(par + 4 * j); t.sc1 = lds_f4(par + 4 * j + 16);
-                    t.sh0 = lds_f4(par + 4 * (HALF + j)); t.sh1 = lds_f4(par + 4 * (HALF + j) + 16);
                     t.r0 = make_float4(0.f, 0.f, 0.f, 0.f); t.r1 = t.r0;
                     if (has_res) {
                         t.r0 = lds_f4(slab_addr(j >> 5, lane, (j >> 2) & 7));
@@ -602,10 +607,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     Step nxt = cur;
                     if (j + 8 < HALF) nxt = load_step(j + 8);
                     float4 x0, x1;
-                    x0.x = fuse(acc[j], cur.sc0.x, cur.sh0.x, cur.r0.x); x0.y = fuse(acc[j + 1], cur.sc0.y, cur.sh0.y, cur.r0.y);
-                    x0.z = fuse(acc[j + 2], cur.sc0.z, cur.sh0.z, cur.r0.z); x0.w = fuse(acc[j + 3], cur.sc0.w, cur.sh0.w, cur.r0.w);
-                    x1.x = fuse(acc[j + 4], cur.sc1.x, cur.sh1.x, cur.r1.x); x1.y = fuse(acc[j + 5], cur.sc1.y, cur.sh1.y, cur.r1.y);
-                    x1.z = fuse(acc[j + 6], cur.sc1.z, cur.sh1.z, cur.r1.z); x1.w = fuse(acc[j + 7], cur.sc1.w, cur.sh1.w, cur.r1.w);
+                    x0.x = fuse(acc[j], cur.r0.x); x0.y = fuse(acc[j + 1], cur.r0.y);
+                    x0.z = fuse(acc[j + 2], cur.r0.z); x0.w = fuse(acc[j + 3], cur.r0.w);
+                    x1.x = fuse(acc[j + 4], cur.r1.x); x1.y = fuse(acc[j + 5], cur.r1.y);
+                    x1.z = fuse(acc[j + 6], cur.r1.z); x1.w = fuse(acc[j + 7], cur.r1.w);
                     sts_f4(a0, x0);
                     sts_f4(a1, x1);
                     cur = nxt;

@@ -967,13 +967,8 @@ int fcp_conv2d(fcp_ctx* ctx, const float* x, int n, int h, int w, int cin, const
     wt.data.assign(weight, weight + (size_t)cout * cin * k * k);
     tmp.host["c.weight"] = wt;
     size_t mark = ctx->device_allocs.size();
-    FCP_TRY(pack_conv(ctx, tmp, {"c"}, "", "c"));
+    FCP_TRY(pack_conv(ctx, tmp, {"c"}, "", "c", scale, shift));
     ConvWeights& cw = tmp.conv["c"];
-    std::vector<float> sc(cw.cout_pad, 1.f), sh(cw.cout_pad, 0.f);
-    if (scale) std::copy(scale, scale + cout, sc.begin());
-    if (shift) std::copy(shift, shift + cout, sh.begin());
-    FCP_CUDA(ctx, cudaMemcpy(cw.scale, sc.data(), sizeof(float) * cw.cout_pad, cudaMemcpyHostToDevice));
-    FCP_CUDA(ctx, cudaMemcpy(cw.shift, sh.data(), sizeof(float) * cw.cout_pad, cudaMemcpyHostToDevice));
     const int ho = odim(h, k, stride, pad), wo = odim(w, k, stride, pad);
     const int cs_out = (cout + 3) / 4 * 4;
     DevIn xin, res;

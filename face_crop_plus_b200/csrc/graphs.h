@@ -6,7 +6,7 @@ namespace fcp {
 
 bool is_device_ptr(const void* p);
 int pack_conv(fcp_ctx* ctx, Model& m, const std::vector<std::string>& convs, const std::string& bn,
-              const std::string& name);
+              const std::string& name, const float* explicit_scale = nullptr, const float* explicit_shift = nullptr);
 
 // tensor-core packing of a 7x7 stem (`conv` = name of the already packed square conv, whose folded BN it shares):
 // weights [64][7 vertical taps][32 = 7 horizontal taps x 3 channels, zero padded], registered as `name`

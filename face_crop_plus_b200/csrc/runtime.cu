@@ -111,7 +111,7 @@ static inline float tf32_trunc(float x) {
 // Packs conv `convs[i].weight` (OIHW, concatenated along Cout) with optional bias and optional BatchNorm `bn`
 // (running stats folded like ATen's eval batch_norm: alpha = gamma/sqrt(var+eps), beta = bias - mean*alpha).
 int pack_conv(fcp_ctx* ctx, Model& m, const std::vector<std::string>& convs, const std::string& bn,
-              const std::string& name) {
+              const std::string& name, const float* explicit_scale, const float* explicit_shift) {
     ConvWeights cw;
     std::vector<const HostTensor*> ws, bs;
     for (auto& c : convs) {
@@ -126,26 +126,16 @@ int pack_conv(fcp_ctx* ctx, Model& m, const std::vector<std::string>& convs, con
     }
     cw.cout_pad = (cw.cout + 31) / 32 * 32;
     const int K = cw.k * cw.k * cw.cin;
-    std::vector<float> wkn((size_t)K * cw.cout_pad, 0.f), scale(cw.cout_pad, 1.f), shift(cw.cout_pad, 0.f);
-    std::vector<float> whi((size_t)cw.cout_pad * K, 0.f), wlo((size_t)cw.cout_pad * K, 0.f);
-    int o0 = 0;
-    for (size_t g = 0; g < ws.size(); ++g) {
-        const HostTensor& w = *ws[g];
-        int co_n = (int)w.shape[0];
-        for (int o = 0; o < co_n; ++o)
-            for (int c = 0; c < cw.cin; ++c)
-                for (int r = 0; r < cw.k; ++r)
-                    for (int s = 0; s < cw.k; ++s) {
-                        float v = w.data[(((size_t)o * cw.cin + c) * cw.k + r) * cw.k + s];
-                        size_t kk = (size_t)(r * cw.k + s) * cw.cin + c;
-                        wkn[kk * cw.cout_pad + o0 + o] = v;
-                        float hi = tf32_trunc(v);
-                        whi[(size_t)(o0 + o) * K + kk] = hi;
-                        wlo[(size_t)(o0 + o) * K + kk] = tf32_trunc(v - hi);
-                    }
-        if (bs[g])
-            for (int o = 0; o < co_n; ++o) shift[o0 + o] = bs[g]->data[o];
-        o0 += co_n;
+    // ---- per-channel affine after the conv: conv bias, then BatchNorm (or the explicit scale/shift of the test hook)
+    std::vector<float> scale(cw.cout_pad, 1.f), shift(cw.cout_pad, 0.f);
+    {
+        int o0 = 0;
+        for (size_t g = 0; g < ws.size(); ++g) {
+            const int co_n = (int)ws[g]->shape[0];
+            if (bs[g])
+                for (int o = 0; o < co_n; ++o) shift[o0 + o] = bs[g]->data[o];
+            o0 += co_n;
+        }
     }
     if (!bn.empty()) {
         const HostTensor *g = find(m, bn + ".weight"), *b = find(m, bn + ".bias"), *mu = find(m, bn + ".running_mean"),
@@ -160,12 +150,40 @@ int pack_conv(fcp_ctx* ctx, Model& m, const std::vector<std::string>& convs, con
             scale[o] = alpha;
         }
     }
+    for (int o = 0; o < cw.cout; ++o) {
+        if (explicit_scale) scale[o] = explicit_scale[o];
+        if (explicit_shift) shift[o] = explicit_shift[o];
+    }
+    // ---- weights.  CUDA-core kernel: [K][cout_pad], plain (it applies scale/shift in its epilogue).  Tensor-core kernel:
+    // K-major [cout_pad][K] with the per-channel SCALE FOLDED IN (w*scale, then split into tf32 hi + lo), so that its
+    // epilogue only adds the shift - done while the K loop still runs, off the tile-boundary critical path.
+    std::vector<float> wkn((size_t)K * cw.cout_pad, 0.f);
+    std::vector<float> whi((size_t)cw.cout_pad * K, 0.f), wlo((size_t)cw.cout_pad * K, 0.f);
+    int o0 = 0;
+    for (size_t g = 0; g < ws.size(); ++g) {
+        const HostTensor& w = *ws[g];
+        int co_n = (int)w.shape[0];
+        for (int o = 0; o < co_n; ++o)
+            for (int c = 0; c < cw.cin; ++c)
+                for (int r = 0; r < cw.k; ++r)
+                    for (int s = 0; s < cw.k; ++s) {
+                        float v = w.data[(((size_t)o * cw.cin + c) * cw.k + r) * cw.k + s];
+                        size_t kk = (size_t)(r * cw.k + s) * cw.cin + c;
+                        wkn[kk * cw.cout_pad + o0 + o] = v;
+                        const float vs = v * scale[o0 + o];
+                        float hi = tf32_trunc(vs);
+                        whi[(size_t)(o0 + o) * K + kk] = hi;
+                        wlo[(size_t)(o0 + o) * K + kk] = tf32_trunc(vs - hi);
+                    }
+        o0 += co_n;
+    }
     FCP_TRY(upload(ctx, wkn, &cw.w_kn));
     FCP_TRY(upload(ctx, whi, &cw.w_hi));
     FCP_TRY(upload(ctx, wlo, &cw.w_lo));
     FCP_TRY(upload(ctx, scale, &cw.scale));
     FCP_TRY(upload(ctx, shift, &cw.shift));
     m.conv[name] = cw;
+    m.vec[name + ".scale"] = scale;
     return FCP_OK;
 }
 
@@ -175,6 +193,8 @@ int pack_stem_rows(fcp_ctx* ctx, Model& m, const std::string& conv, const std::s
     if (!w || w->shape.size() != 4 || w->shape[1] != 3 || w->shape[2] != 7 || w->shape[3] != 7 || it == m.conv.end())
         return fail(ctx, FCP_ERR_STATE, "stem weights missing or not 7x7x3: " + conv);
     ConvWeights cw = it->second;                       // shares scale / shift (folded BN) with the square packing
+    const std::vector<float>& scale = m.vec[conv + ".scale"];
+    if ((int)scale.size() < cw.cout) return fail(ctx, FCP_ERR_STATE, "stem scale missing: " + conv);
     cw.cin = 32; cw.k = 7; cw.kh = 7; cw.kw = 1; cw.alg_k = 147;
     cw.w_kn = nullptr;                                 // no CUDA-core packing: this route exists on the tensor cores only
     const int K = 7 * 32;
@@ -183,7 +203,7 @@ int pack_stem_rows(fcp_ctx* ctx, Model& m, const std::string& conv, const std::s
         for (int c = 0; c < 3; ++c)
             for (int r = 0; r < 7; ++r)
                 for (int sx = 0; sx < 7; ++sx) {
-                    const float v = w->data[(((size_t)o * 3 + c) * 7 + r) * 7 + sx];
+                    const float v = w->data[(((size_t)o * 3 + c) * 7 + r) * 7 + sx] * scale[o];   // folded BN scale, like pack_conv
                     const size_t kk = (size_t)r * 32 + sx * 3 + c;
                     const float hi = tf32_trunc(v);
                     whi[(size_t)o * K + kk] = hi;
