@@ -66,7 +66,9 @@ struct alignas(64) TcParams {
     int act; float slope;
     float post_scale; const float* res2; int res2_cs, res2_co, res2_h, res2_w;
     float post_scale2; const float* res3; int res3_cs, res3_co;
-    int exp_nolo;                              // experiment: skip the w_lo loads (wrong results; L2-traffic probe)
+    int ablate;                                // FCP_TC_ABLATE bit mask, measurement only (results are WRONG with bits 1/2):
+                                               //   1 skip the w_lo loads (L2->SM / smem-write traffic probe), 2 skip the bulk stores,
+                                               //   16 back-off in the drain warps' d_full wait
     long long* dbg;                            // FCP_EXP_TIMELINE: clock64 stamps of CTA 0, [g][16]
 };
 
@@ -132,12 +134,6 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
 __device__ __forceinline__ void sts_f4(uint32_t addr, const float4& v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
-__device__ __forceinline__ void sts_f1(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
-__device__ __forceinline__ float lds_f1(uint32_t addr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
-    return v;
-}
 #ifdef FCP_EXP_TIMELINE
 #define TL(g, ev) do { if (p.dbg && blockIdx.x == 0 && (g) < 512) p.dbg[(g) * 16 + (ev)] = clock64(); } while (0)
 #else
@@ -148,12 +144,8 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 // generic-proxy writes to shared memory -> visible to the async proxy (TMA store source)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, one CTA
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
-                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// same with the A operand in tensor memory (rows = lanes, one 32-bit column per tf32 element)
+// D[tmem] (+)= A[tmem] * B[smem desc], kind::tf32, one CTA: A operand in tensor memory (rows = lanes, one 32-bit column
+// per tf32 element), B through a shared-memory descriptor
 __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}"
                  ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
@@ -173,22 +165,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// 32 lanes x N consecutive 32-bit columns: thread i of the warp receives lane (base_lane + i)
-template <int N> __device__ __forceinline__ void tmem_ld(uint32_t taddr, float* v);
-template <> __device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, float* v) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
+// 32 lanes x 16 consecutive 32-bit columns: thread i of the warp receives lane (base_lane + i).
 // issue only (no wait): the caller overlaps the load with arithmetic on the previous piece and then calls tmem_ld_wait()
 __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
     asm volatile(
@@ -198,18 +175,6 @@ __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
         : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-template <> __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float* v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row atoms 1024 bytes apart (SBO), LBO unused (=1),
 // descriptor version 1 (Blackwell), layout type 2 (SWIZZLE_128B).
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
@@ -217,12 +182,6 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
            ((uint64_t)2 << 61);
 }
 
-__device__ __forceinline__ float act_fn(float v, int act, float slope) {
-    if (act == FCP_ACT_RELU) return fmaxf(v, 0.f);
-    if (act == FCP_ACT_LRELU) return v > 0.f ? v : v * slope;
-    if (act == FCP_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
-    return v;
-}
 
 // Epilogue data path.  The 4 epilogue warps that share a channel half (one warp per TMEM lane quarter = 32 pixels) own a
 // shared-memory slab of CHUNKS x [128 pixels][32 channels] fp32 in the 128B-swizzled layout TMA produces (16-byte piece c
@@ -336,9 +295,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     mbar_expect_tx(&full_a[land], A_TILE_BYTES);
                     tma_load_4d(landing(land), &p.tmA[map], &full_a[land], c0, wo0 + dx, ho0 + dy, img);
                     mbar_wait<true>(&empty[stage], phase ^ 1);
-                    mbar_expect_tx(&full_b[stage], ((p.exp_nolo & 1) ? 1 : 2) * C::B_TILE_BYTES);
+                    mbar_expect_tx(&full_b[stage], ((p.ablate & 1) ? 1 : 2) * C::B_TILE_BYTES);
                     tma_load_2d(stage_b_hi(stage), &p.tmBhi, &full_b[stage], kcol, n_tile * BN);
-                    if (!(p.exp_nolo & 1)) tma_load_2d(stage_b_lo(stage), &p.tmBlo, &full_b[stage], kcol, n_tile * BN);
+                    if (!(p.ablate & 1)) tma_load_2d(stage_b_lo(stage), &p.tmBlo, &full_b[stage], kcol, n_tile * BN);
                     if (++cc == cchunks) { cc = 0; ++tap; if (++sx == p.KW) { sx = 0; ++r; } }
                     TL(gp, 1); ++gp;
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -529,7 +488,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             };
             if (warp == 6 && lane == 0) TL(g, 13);                            // tile prologue (params, residual prefetch) issued
             for (int kb = 0; kb < kblocks; ++kb, ++g) {
-                if (p.exp_nolo & 16) mbar_wait<true>(&d_full[buf], dpar);
+                if (p.ablate & 16) mbar_wait<true>(&d_full[buf], dpar);
                 else mbar_wait(&d_full[buf], dpar);
                 if (warp == 6 && lane == 0) TL(g, 7);
                 tc_fence_after();
@@ -624,7 +583,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 fence_async_smem();
                 group_sync();                                                 // all 128 pixel rows of the group's chunks are final
                 if (warp == 6 && lane == 0) TL(g - 1, 12);
-                if (dma && !(p.exp_nolo & 2)) {
+                if (dma && !(p.ablate & 2)) {
                     if (n0 + quarter * 32 < p.Cout) tma_store_4d(&p.tmOut, S + quarter * C::CHUNK_BYTES, n0 + quarter * 32, wo0, ho0, img);
                     bulk_commit();
                 }
@@ -800,8 +759,8 @@ int launch_conv_tc(fcp_ctx* ctx, const ConvOp& op) {
     p.act = op.act; p.slope = op.slope;
     p.post_scale = op.post_scale; p.res2 = op.res2; p.res2_cs = op.res2_cs; p.res2_co = op.res2_co; p.res2_h = op.res2_h; p.res2_w = op.res2_w;
     p.post_scale2 = op.post_scale2; p.res3 = op.res3; p.res3_cs = op.res3_cs; p.res3_co = op.res3_co;
-    static const int exp_nolo = getenv("FCP_EXP_NOLO") ? atoi(getenv("FCP_EXP_NOLO")) : 0;
-    p.exp_nolo = exp_nolo;
+    static const int ablate = getenv("FCP_TC_ABLATE") ? atoi(getenv("FCP_TC_ABLATE")) : 0;
+    p.ablate = ablate;
     auto do_launch = [&]() -> int {
         if (BN == 128) return launch<128>(ctx, p);
         if (BN == 64) return launch<64>(ctx, p);
