@@ -123,9 +123,15 @@ class Cropper:
                 ldm_rows += rows.tolist()
             landmarks = self.landmarks[0][ldm_rows]
         else:
-            images, _, paddings = as_batch(images, self.resize_size, ctx=self.ctx)
             if self.enh_model is None:
-                return self._process_detected_batch(images, paddings, file_names, output_dir)
+                # ingest straight into a device batch: resize + pad (fcp_as_batch) and the detect -> align -> parse call
+                # share it, the images never come back to the host between the two
+                batch = torch.empty((len(images), self.resize_size[1], self.resize_size[0], 3), dtype=torch.uint8,
+                                    device=self.device)
+                with _lock:
+                    _, _, paddings = self.ctx.as_batch(images, self.resize_size, out=batch)
+                return self._process_detected_batch(batch, paddings, file_names, output_dir)
+            images, _, paddings = as_batch(images, self.resize_size, ctx=self.ctx)
             landmarks, indices = self.det_model.predict_u8(images)
             landmarks = landmarks - paddings[indices][:, None, [2, 0]] if len(indices) else landmarks   # :822
         if landmarks is not None and len(landmarks) == 0:
@@ -153,7 +159,8 @@ class Cropper:
         with _lock:
             if self.par_model is not None:
                 self.ctx.set_micro_batch(16, max(int(self.batch_size), 1))
-            out = self.ctx.pipeline(np.ascontiguousarray(images), paddings, self.landmarks_target, self.output_size,
+            batch = images if hasattr(images, "data_ptr") else np.ascontiguousarray(images)
+            out = self.ctx.pipeline(batch, paddings, self.landmarks_target, self.output_size,
                                     self.det_threshold, self.det_model.nms_threshold, self.strategy, self.padding,
                                     self.allow_skew, parse=self.par_model is not None)
         if out["count"] == 0:
