@@ -44,6 +44,7 @@ SIGNATURES = {
     "fcp_detect_post": (_i, [_p, _p, _i, _i, _i, _f, _f, _i, _i, _p, _p, _p, _p, _p, _p]),
     "fcp_align": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _i, _p, _i, _i, _i, _i, _p, _p, _p]),
     "fcp_align_list": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _i, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "fcp_reduce_landmarks": (_i, [_p, _p, _i, _i, _p]),
     "fcp_as_batch": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "fcp_parse": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "fcp_parse_logits": (_i, [_p, _p, _i, _i, _i, _p]),
@@ -226,6 +227,17 @@ class Context:
             self.check(self.lib.fcp_align(self.h, _ptr(images), n, h, w, _ptr(pad), _ptr(idx), _ptr(lms), f, _ptr(tgt), ow, oh,
                                           bm, int(allow_skew), _ptr(crops), _ptr(mats), _ptr(valid)))
         return crops, mats, valid.astype(bool)
+
+    def reduce_landmarks(self, landmarks):
+        """f32 [F,K,2] -> f32 [F,5,2]: slice means of utils.py:90-168 / cropper.py:828-831 (ValueError for an unsupported K)."""
+        lms = np.ascontiguousarray(landmarks, dtype=np.float32)
+        f, k = lms.shape[:2]
+        out = np.empty((f, 5, 2), np.float32)
+        code = self.lib.fcp_reduce_landmarks(self.h, _ptr(lms), f, k, _ptr(out))
+        if code == ERR_INVALID:
+            raise ValueError((self.lib.fcp_last_error(self.h) or b"").decode())
+        self.check(code)
+        return out
 
     # ---- ingest
     def as_batch(self, images, size=512, padding_mode="constant", out=None):

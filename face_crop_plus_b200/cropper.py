@@ -137,8 +137,9 @@ class Cropper:
         if landmarks is not None and len(landmarks) == 0:
             return
         if landmarks is not None and landmarks.shape[1] != self.num_std_landmarks:
-            slices = get_ldm_slices(self.num_std_landmarks, landmarks.shape[1])
-            landmarks = np.stack([landmarks[:, s].mean(1) for s in slices], 1)
+            get_ldm_slices(self.num_std_landmarks, landmarks.shape[1])        # ValueError for unsupported counts, like the reference
+            with _lock:
+                landmarks = self.ctx.reduce_landmarks(landmarks)               # the slice means, on the device
         if self.enh_model is not None:
             if isinstance(images, np.ndarray):
                 x = torch.from_numpy(images).to(self.enh_model.device).permute(0, 3, 1, 2).float().contiguous()

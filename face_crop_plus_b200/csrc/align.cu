@@ -200,4 +200,27 @@ int launch_warp(fcp_ctx* ctx, const uint8_t* images, int n, int h, int w, const 
     return FCP_OK;
 }
 
+// N-point -> 5-point landmark reduction (utils.py:90-168, cropper.py:828-831): point j of the result is the float32 mean of
+// the source points [lo_j, hi_j) - summed in index order, then divided by the count, exactly what
+// ``landmarks[:, s].mean(1)`` does on a float32 [F,K,2] array.
+__global__ void reduce_landmarks_kernel(const float* __restrict__ lms, int f, int k, int lo0, int hi0, int lo1, int hi1, int lo2,
+                                        int hi2, int lo3, int hi3, int lo4, int hi4, float* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= f * 10) return;
+    const int face = idx / 10, r = idx - face * 10, j = r >> 1, c = r & 1;
+    const int lo = j == 0 ? lo0 : j == 1 ? lo1 : j == 2 ? lo2 : j == 3 ? lo3 : lo4;
+    const int hi = j == 0 ? hi0 : j == 1 ? hi1 : j == 2 ? hi2 : j == 3 ? hi3 : hi4;
+    float acc = 0.f;
+    for (int i = lo; i < hi; ++i) acc = __fadd_rn(acc, lms[((size_t)face * k + i) * 2 + c]);
+    out[idx] = __fdiv_rn(acc, (float)(hi - lo));
+}
+
+int launch_reduce_landmarks(fcp_ctx* ctx, const float* lms, int f, int k, const int bounds[10], float* out) {
+    if (f == 0) return FCP_OK;
+    reduce_landmarks_kernel<<<(f * 10 + 127) / 128, 128, 0, ctx->stream>>>(lms, f, k, bounds[0], bounds[1], bounds[2], bounds[3], bounds[4],
+                                                                         bounds[5], bounds[6], bounds[7], bounds[8], bounds[9], out);
+    FCP_KERNEL_CHECK(ctx);
+    return FCP_OK;
+}
+
 }  // namespace fcp

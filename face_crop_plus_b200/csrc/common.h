@@ -161,6 +161,8 @@ int run_conv(fcp_ctx* ctx, const ConvOp& op);
 // (retinaface.py:450-451); mode 1: src = f32 NHWC 3-channel
 int launch_stem7(fcp_ctx* ctx, const void* src, int mode, int n, int h, int w, const float* w_kn /*[147][64]*/,
                  const float* scale, const float* shift, Tensor out);
+// 5-point means of an N-point annotation; bounds = {lo0, hi0, ..., lo4, hi4} (utils.py:90-132)
+int launch_reduce_landmarks(fcp_ctx* ctx, const float* lms, int f, int k, const int bounds[10], float* out);
 // batch ingest (utils.as_batch): resize (OpenCV INTER_AREA / INTER_CUBIC arithmetic) + centred padding of a ragged image list;
 // dev_ptrs[i] = device u8 [hs[i], ws[i], 3]; out = device u8 [n, size_h, size_w, 3]; unscales / paddings are HOST outputs
 int launch_ingest(fcp_ctx* ctx, const uint8_t* const* dev_ptrs, const int32_t* hs, const int32_t* ws, int n, int size_w,

@@ -686,6 +686,31 @@ int fcp_align_list(fcp_ctx* ctx, const uint8_t* const* image_ptrs, const int32_t
                      border_mode, allow_skew, out_crops, out_matrices, out_valid);
 }
 
+int fcp_reduce_landmarks(fcp_ctx* ctx, const float* landmarks, int f, int k, float* out) {
+    // utils.py:90-132: which source points are averaged into each of the 5 standard landmarks
+    static const struct { int k; int b[10]; } table[] = {
+        {5, {0, 1, 1, 2, 2, 3, 3, 4, 4, 5}},          {12, {10, 11, 11, 12, 2, 3, 3, 4, 4, 5}},
+        {17, {2, 5, 7, 10, 10, 11, 13, 14, 16, 17}},  {21, {6, 9, 9, 12, 14, 15, 17, 18, 19, 20}},
+        {29, {4, 9, 13, 18, 19, 20, 22, 23, 27, 28}}, {49, {19, 25, 25, 31, 13, 14, 31, 32, 37, 38}},
+        {68, {36, 42, 42, 48, 30, 31, 48, 49, 54, 55}}, {98, {60, 68, 68, 76, 54, 55, 76, 77, 82, 83}},
+        {106, {66, 75, 75, 84, 54, 55, 85, 86, 91, 92}}};
+    if (!ctx || f < 0 || (f && (!landmarks || !out))) return fail(ctx, FCP_ERR_INVALID, "fcp_reduce_landmarks: bad argument");
+    const int* bounds = nullptr;
+    for (auto& t : table)
+        if (t.k == k) bounds = t.b;
+    if (!bounds) return fail(ctx, FCP_ERR_INVALID, "Invalid number of landmarks: " + std::to_string(k));
+    FCP_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (f == 0) return FCP_OK;
+    DevIn in;
+    FCP_TRY(in.init(ctx, landmarks, sizeof(float) * 2 * k * f));
+    DevOut o;
+    FCP_TRY(o.init(ctx, out, sizeof(float) * 10 * f));
+    FCP_TRY(launch_reduce_landmarks(ctx, in.as<float>(), f, k, bounds, o.as<float>()));
+    FCP_TRY(o.flush());
+    FCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FCP_OK;
+}
+
 int fcp_as_batch(fcp_ctx* ctx, const uint8_t* const* image_ptrs, const int32_t* hs, const int32_t* ws, int n, int size_w,
                  int size_h, int border_mode, uint8_t* out_batch, double* out_unscales, int32_t* out_paddings) {
     if (!ctx || n < 0 || size_w < 1 || size_h < 1 || border_mode < 0 || border_mode > 4 || (n && (!image_ptrs || !hs || !ws || !out_batch)))

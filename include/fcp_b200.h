@@ -115,6 +115,11 @@ int fcp_align_list(fcp_ctx* ctx, const uint8_t* const* image_ptrs, const int32_t
                    const float* target, int out_w, int out_h, int border_mode, int allow_skew, uint8_t* out_crops,
                    double* out_matrices, uint8_t* out_valid);
 
+/* N-point -> 5-point landmark reduction: replaces get_ldm_slices + the slice means of Cropper.process_batch
+ * (utils.py:90-168, cropper.py:828-831).  landmarks f32 [f,k,2] with k in {5,12,17,21,29,49,68,98,106} (any other k:
+ * FCP_ERR_INVALID, where the reference raises ValueError); out f32 [f,5,2] = (left eye, right eye, nose, mouth corners). */
+int fcp_reduce_landmarks(fcp_ctx* ctx, const float* landmarks, int f, int k, float* out);
+
 /* ---- parse: replaces BiSeNet.predict (models/bise.py:327-418) -------------------------------------------
  * crops u8 [f,h,w,3]; out_labels u8 [f,h,w] (argmax class 0..18), out_hist i32 [f,19] pixel count per class
  * (either may be NULL).  Grouping by thresholds (bise.py:214-325) is integer work on out_hist done by the host;

@@ -99,3 +99,23 @@ def test_model_shims_follow_reference_contracts(state_dicts, golden):
     enh = RRDBNet(0.02).load("cuda:0", state_dicts["enh"])
     out = enh.predict(xe, ge["landmarks"], ge["indices"].tolist())
     assert out is xe and np.abs(out.numpy() - ge["predict"]).max() <= 1
+
+
+@pytest.mark.parametrize("k", [5, 12, 17, 21, 29, 49, 68, 98, 106])
+def test_reduce_landmarks_bit_exact(k):
+    """fcp_reduce_landmarks == the slice means of cropper.py:828-831 (float32 ``landmarks[:, s].mean(1)``), bit for bit."""
+    from face_crop_plus_b200 import utils
+    from face_crop_plus_b200.models import get_context
+    ctx = get_context("cuda:0")
+    rng = np.random.default_rng(k)
+    lms = (rng.random((37, k, 2)) * 1000).astype(np.float32)
+    ref = np.stack([lms[:, s].mean(1) for s in utils.get_ldm_slices(5, k)], 1)
+    got = ctx.reduce_landmarks(lms)
+    assert got.dtype == np.float32 and np.array_equal(got, ref)
+
+
+def test_reduce_landmarks_rejects_unknown_counts():
+    from face_crop_plus_b200.models import get_context
+    with pytest.raises(ValueError):
+        get_context("cuda:0").reduce_landmarks(np.zeros((2, 7, 2), np.float32))
+    assert get_context("cuda:0").reduce_landmarks(np.zeros((0, 68, 2), np.float32)).shape == (0, 5, 2)
