@@ -75,3 +75,28 @@ def test_as_batch_vs_reference_golden(ci):
     assert np.array_equal(unscales, GOLD[f"c{ci}_unscales"]) and np.array_equal(paddings, GOLD[f"c{ci}_paddings"])
     d = GOLD[f"c{ci}_ipp_minus_cv"]                                             # reference as this image runs it (IPP cubic)
     assert np.abs(d).max() <= 1
+
+
+def test_random_shapes_property():
+    """Randomised pin (seeded): any shrink through INTER_AREA and any resize through INTER_CUBIC equals cv2, plus the as_batch
+    plan (sizes, paddings, interpolation choice) against cv2 called the way utils.py:317-335 calls it."""
+    cv2.ipp.setUseIPP(False)
+    rng = np.random.default_rng(2024)
+    for _ in range(120):
+        sh, sw = int(rng.integers(2, 90)), int(rng.integers(2, 90))
+        img = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        dh, dw = int(rng.integers(1, sh + 1)), int(rng.integers(1, sw + 1))
+        assert np.array_equal(ingest.resize_area(img, dw, dh), cv2.resize(img, (dw, dh), interpolation=cv2.INTER_AREA)), (sh, sw, dh, dw)
+        dh, dw = int(rng.integers(1, 150)), int(rng.integers(1, 150))
+        assert np.array_equal(ingest.resize_cubic(img, dw, dh), cv2.resize(img, (dw, dh), interpolation=cv2.INTER_CUBIC)), (sh, sw, dh, dw)
+    for _ in range(40):
+        imgs = [rng.integers(0, 256, (int(rng.integers(8, 120)), int(rng.integers(8, 120)), 3), dtype=np.uint8) for _ in range(3)]
+        size = (int(rng.integers(16, 100)), int(rng.integers(16, 100)))
+        mode = list(ingest.BORDER_MODES)[int(rng.integers(0, 5))]
+        batch, _, pads = ingest.as_batch(imgs, size, mode)
+        for i, im in enumerate(imgs):
+            h, w = im.shape[:2]
+            nw, nh, _, pad, interp = ingest.plan(h, w, size)
+            ref = cv2.resize(im, (nw, nh), interpolation=cv2.INTER_AREA if interp == "area" else cv2.INTER_CUBIC)
+            ref = cv2.copyMakeBorder(ref, *pad, borderType=getattr(cv2, "BORDER_" + mode.upper()))
+            assert np.array_equal(batch[i], ref) and pads[i].tolist() == pad
