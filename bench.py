@@ -262,7 +262,10 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                 "roofline": {"bound": "tensor", "kernel": "conv (all launches of the step)", "achieved": conv_tflops,
                              "peak": tensor_peak, "unit": "TFLOP/s", "frac": conv_tflops / tensor_peak,
                              "peak_source": f"{which} bf16 sustained; the kernel is exact-fp32 (parity bar), see DESIGN.md",
-                             "traffic": None, "conv_launches_per_step": prof["conv_launches"] // args.steps,
+                             "traffic": None,
+                             # an fp32-equivalent result costs 3 TF32 MMAs at half the bf16 rate: ceiling = peak / 6
+                             "frac_of_3xtf32_ceiling": conv_tflops / (tensor_peak / 6.0),
+                             "conv_launches_per_step": prof["conv_launches"] // args.steps,
                              "conv_ms_per_step": prof["conv_ms"] / args.steps,
                              "conv_share_of_step": prof["conv_ms"] / ms_total,
                              "algorithmic_gflop_per_image": prof["conv_flops"] / args.steps / B / 1e9},
