@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--class-bias", type=float, default=4.8)
     ap.add_argument("--det-mb", type=int, default=16)
     ap.add_argument("--par-mb", type=int, default=32)
-    ap.add_argument("--conv-impl", type=int, default=int(os.environ.get("FCP_CONV_IMPL", "1")))
+    ap.add_argument("--conv-impl", type=int, default=int(os.environ.get("FCP_CONV_IMPL", "2")))
     ap.add_argument("--cpu-sample", type=int, default=4, help="images in the cpu_baseline sample (0 = skip)")
     return ap.parse_args()
 
@@ -252,7 +252,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                 "data": "synthetic",
                 "config": {"workload": f"detect+align+parse, {S}x{S} uint8 RGB, bs={B} per GPU, strategy=largest, 256x256 crops",
                            "global_batch": world * B, "faces_per_step_per_gpu": faces, "class_bias": args.class_bias,
-                           "conv_impl": "tcgen05-3xTF32" if args.conv_impl else "cuda-core-fp32",
+                           "conv_impl": ["cuda-core-fp32", "tcgen05-3xTF32", "tcgen05-3xFP16-block-scaled"][args.conv_impl],
                            "micro_batch": [args.det_mb, args.par_mb], "parallelism": f"batch-shard x{world}",
                            "l2": f"inputs larger than L2 ({B * S * S * 3 / 2**20:.0f} MiB batch; activations stream through a "
                                  f"micro-batched arena)"},

@@ -40,6 +40,11 @@ struct ConvWeights {
     float* w_kn = nullptr;     // device [k*k*cin][cout_pad]  (row = (r*k+s)*cin + c), CUDA-core kernel
     float* w_hi = nullptr;     // device [cout_pad][k*k*cin] K-major, tf32-truncated part   (tcgen05 kernel)
     float* w_lo = nullptr;     // device [cout_pad][k*k*cin] K-major, residual part          (tcgen05 kernel)
+    // tcgen05 kernel, f16x3 mode: w * scale * 2^w_exp split into fp16 hi + lo, K-major [cout_pad][taps * cin_p]
+    void* h_hi = nullptr;
+    void* h_lo = nullptr;
+    int cin_p = 0;             // cin rounded up to 64 (one K-block = 64 channels)
+    int w_exp = 0;
     float* scale = nullptr;    // device [cout_pad]
     float* shift = nullptr;    // device [cout_pad]
 };
@@ -58,7 +63,8 @@ struct ConvOp {
     int res2_h = 0, res2_w = 0;                                             // != 0: res2 is [n,res2_h,res2_w,*], read through a nearest resize
     float post_scale2 = 1.f;
     const float* res3 = nullptr; int res3_cs = 0, res3_co = 0;              // added after (..)*post_scale2
-    int impl = 0;              // 0 CUDA-core fp32, 1 tcgen05 3xTF32
+    int a_exact = 0;           // the input values are small integers (u8 - mean): the split's low part is zero
+    int impl = 0;              // 0 CUDA-core fp32, 1 tcgen05 3xTF32, 2 tcgen05 3xFP16 block-scaled
 };
 
 // ----------------------------------------------------------------------------------------------------------
@@ -111,7 +117,8 @@ struct fcp_ctx {
     std::vector<void*> device_allocs;   // weights etc. freed at destroy
     void* pinned = nullptr; size_t pinned_bytes = 0;
     int sm_count = 148;
-    int use_tc = 1;            // conv implementation of the model graphs: 1 tcgen05 3xTF32 (default), 0 CUDA-core fp32
+    int use_tc = 2;            // conv implementation of the model graphs: 2 tcgen05 3xFP16 block-scaled (default),
+                               // 1 tcgen05 3xTF32, 0 CUDA-core fp32
     // profiling (fcp_profile): event pairs around conv launches + algorithmic work counters
     bool profile = false;
     std::vector<cudaEvent_t> prof_events;   // start0, stop0, start1, stop1, ...

@@ -219,10 +219,10 @@ conv_ffma_kernel(const ConvArgs a) {
 template <int BN>
 int launch(fcp_ctx* ctx, const ConvArgs& a) {
     size_t smem = (size_t)STAGES * (BM * A_LD + BK * BN) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    static uint64_t configured = 0;                    // one bit per device: the attribute is per device
+    if (!((configured >> (ctx->device & 63)) & 1)) {
         FCP_CUDA(ctx, cudaFuncSetAttribute(conv_ffma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured |= (uint64_t)1 << (ctx->device & 63);
     }
     dim3 grid((a.M + BM - 1) / BM, (a.cout_pad + BN - 1) / BN);
     conv_ffma_kernel<BN><<<grid, THREADS, smem, ctx->stream>>>(a);

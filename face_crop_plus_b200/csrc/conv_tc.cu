@@ -31,7 +31,18 @@
 //   warps 6-13  accumulate+epilogue   d_empty[b] <- 8 arrivals (1/warp) (wait d_full[b]); per K-block TMEM -> regs (+=),
 //               after the last K-block: fused epilogue -> HBM.  Warp w owns TMEM lanes 32*(w%4).. and half of the columns.
 // Two TMEM partial-sum buffers let the drain of K-block i overlap the MMAs of K-block i+1.
+//
+// MODE 1 (default, "f16x3"): the same split scheme on the kind::f16 pipe, which runs at twice the TF32 rate.  fp16 has the
+//   same 11-bit significand as TF32 but only a 5-bit exponent, so the operands are BLOCK-SCALED by exact powers of two:
+//   weights once per layer on the host (max |w*bn_scale| -> [2^13, 2^14)), activations per (pixel row, K-block) by the
+//   converter warps (row max -> [2^14, 2^15)); hi = rn_f16(x*s), lo = rn_f16(x*s - hi) (round-to-nearest split: the
+//   representation error is <= 2^-23 relative, 4x smaller than the truncating TF32 split).  The inverse scale of the row
+//   travels through a 16-slot ring in tensor memory to the drain warps, which fold it into the per-K-block accumulate
+//   (acc = fma(partial, 2^-k, acc): exact scaling, one rounding - the same rounding the TF32 mode's add performs).
+//   A K-block is 64 channels (two 32-channel TMA boxes -> one 128-byte fp16 row per operand) = 4 K=16 steps x 3 MMAs, the
+//   same 12 MMAs per drain as MODE 0 for twice the K.  Accuracy vs fp64: tests/test_gpu_parity.py (f16x3 <= tf32x3 <= fp32 FMA).
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cstdio>
 #include <cstdlib>
 #include <type_traits>
@@ -59,6 +70,10 @@ struct alignas(64) TcParams {
     CUtensorMap tmOut, tmRes;                  // output / residual tensor, box = the tile's 128 pixels x 32 channels
     int out_tma, res_tma;                      // epilogue data paths: bulk tensor store / load usable for this launch
     int N, Ho, Wo, Cout, Cin, KH, KW, stride, pad, stride_w, pad_w;   // stride / pad: vertical; *_w: horizontal
+    int cin_p;                                 // channels per tap in the packed weight matrix (MODE 1: Cin rounded up to 64)
+    int w_exp;                                 // MODE 1: the packed weights are w * 2^w_exp
+    int a_exact;                               // the activations are exactly representable in 11 significant bits (u8 - mean):
+                                               //   a_lo == 0, the a_lo*w_hi MMAs are skipped
     int tiles_x, tiles_y, tiles_n, num_tiles, bw_log2, BH;
     float* out; int out_cs, out_co;
     const float* scale; const float* shift;
@@ -150,6 +165,24 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}"
                  ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same, kind::f16: A = packed fp16 pairs in tensor memory (one 32-bit column = K elements 2j (low half), 2j+1), K = 16
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(r) : "memory");
+}
+__device__ __forceinline__ void tmem_ld1_issue(uint32_t taddr, uint32_t& r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+}
 // 32 lanes x 32 columns: thread i of the warp writes its 32 registers to lane (base_lane + i)
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
     asm volatile(
@@ -195,22 +228,31 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
 // ~2300 instructions per warp and tile on address arithmetic and was the bound of every layer with a short K loop.
 // Fallbacks (rolled loops): resized residual (FPN top-down add) via cp.async, per-thread stores when the output is
 // not 16-byte addressable (19-class logits) or carries the RRDB second residual.
-template <int BN> struct Cfg {
-    static constexpr int B_TILE_BYTES = BN * KB * 4;
+template <int BN, int MODE> struct Cfg {
+    static constexpr int KBLK = MODE ? 64 : 32;                           // channels per K-block (one 128-byte operand row)
+    static constexpr int HALVES = MODE ? 2 : 1;                           // 32-channel fp32 landing units (TMA boxes) per K-block
+    static constexpr int B_TILE_BYTES = BN * 128;                         // BN rows x (32 tf32 | 64 fp16)
     static constexpr int B_SLOT_BYTES = 2 * B_TILE_BYTES;                 // w_hi + w_lo of one K-block
     // The K loop is bound by the latency of one trip round the pipeline (TMA issue + landing + convert + MMA issue +
     // retire ~ 3300 cycles, measured) divided by its depth, not by any bandwidth.  The fp32 A tile only lives from its
-    // landing to its conversion, so it gets its own short ring (LANDINGS); a pipeline STAGE is a weight slot in shared
-    // memory plus an (a_hi | a_lo) slot in tensor memory, both held until the K-block's MMAs retire.
-    static constexpr int STAGES = BN >= 128 ? 4 : (BN == 64 ? 5 : 6);
-    static constexpr int LANDINGS = BN >= 128 ? 2 : 3;
+    // landing to its conversion, so it gets its own short ring (LANDINGS units of 16 KiB); a pipeline STAGE is a weight
+    // slot in shared memory plus an (a_hi | a_lo) slot in tensor memory, both held until the K-block's MMAs retire.
+    static constexpr int STAGES = MODE ? (BN >= 128 ? 3 : (BN == 64 ? 4 : 6)) : (BN >= 128 ? 4 : (BN == 64 ? 5 : 6));
+    static constexpr int LANDINGS = MODE ? (BN >= 128 ? 4 : 6) : (BN >= 128 ? 2 : 3);
     // One tcgen05.mma costs its issuing thread ~85 cycles whatever N is, so the narrow BN = 64 tiles (32-cycle MMAs) are
-    // issue-bound: BN <= 64 gets a third issuer + accumulator and one stage less (tensor memory is 512 columns).
+    // issue-bound: BN <= 64 gets a third issuer + accumulator (tensor memory is 512 columns).
     static constexpr int ISSUERS = BN <= 64 ? 3 : 2;
-    // tensor memory: [0, ISSUERS*BN) partial-sum buffers; then STAGES x (a_hi 32 cols | a_lo 32 cols)
+    // tensor memory: [0, ISSUERS*BN) partial-sum buffers; then STAGES x (a_hi 32 cols | a_lo 32 cols); MODE 1: then the
+    // ring of per-row inverse scales (one column per K-block in flight).  A scale slot is rewritten SCALE_SLOTS K-blocks
+    // later; the converter of K-block g' waits for the retirement of K-block g' - STAGES, whose MMAs were issued after the
+    // drain of K-block g' - STAGES - ISSUERS (and, the drain being in order, of every earlier one) had finished:
+    // SCALE_SLOTS >= STAGES + ISSUERS makes the slot of K-block g safe to overwrite.
     static constexpr int TMEM_A0 = ISSUERS * BN;
+    static constexpr int TMEM_SC0 = TMEM_A0 + STAGES * 64;
+    static constexpr int SCALE_SLOTS = 16;
     static constexpr int TMEM_COLS = 512;
-    static_assert(TMEM_A0 + STAGES * 64 <= TMEM_COLS, "tensor memory budget");
+    static_assert(TMEM_SC0 + (MODE ? SCALE_SLOTS : 0) <= TMEM_COLS, "tensor memory budget");
+    static_assert(SCALE_SLOTS >= STAGES + ISSUERS, "scale ring too short");
     static constexpr int EPI_WARPS = BN >= 64 ? 8 : 4;                    // BN=32: one warp per TMEM lane quarter
     static constexpr int HALF = BN >= 64 ? BN / 2 : BN;                   // channels owned by one epilogue warp
     static constexpr int GROUPS = EPI_WARPS / 4;                          // 4 warps (all 128 pixels) share HALF channels
@@ -224,9 +266,9 @@ template <int BN> struct Cfg {
     static_assert(B_SLOT_BYTES % 1024 == 0 && B_TILE_BYTES % 1024 == 0, "operand tiles must stay 1024-byte aligned (swizzle atoms)");
 };
 
-template <int BN>
+template <int BN, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, MODE>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     // [STAGES x (w_hi | w_lo)] [LANDINGS x fp32 A tile] [slab: GROUPS x CHUNKS x 128 rows x 128 B] [params] [barriers]
@@ -262,7 +304,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
 
-    const int cchunks = p.Cin / KB;
+    const int cchunks = (p.Cin + C::KBLK - 1) / C::KBLK;
     const int kblocks = p.KH * p.KW * cchunks;
     const int BW = 1 << p.bw_log2;
     const int tiles_per_img = p.tiles_x * p.tiles_y;
@@ -288,12 +330,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                         map += px;
                         dx = (dx - px) >> 1;
                     }
-                    const int c0 = cc * KB, kcol = tap * p.Cin + c0;
-                    // the activation tile first (it has the longer way to go: landing -> converters -> tensor memory)
-                    mbar_wait<true>(&a_free[land], lphase ^ 1);
-                    TL(gp, 0);
-                    mbar_expect_tx(&full_a[land], A_TILE_BYTES);
-                    tma_load_4d(landing(land), &p.tmA[map], &full_a[land], c0, wo0 + dx, ho0 + dy, img);
+                    const int c0 = cc * C::KBLK, kcol = tap * p.cin_p + c0;
+                    // the activation tile first (it has the longer way to go: landing -> converters -> tensor memory);
+                    // MODE 1: two 32-channel boxes per K-block (the second one is skipped past the last channel)
+#pragma unroll
+                    for (int hf = 0; hf < C::HALVES; ++hf) {
+                        if (hf && c0 + 32 >= p.Cin) break;
+                        mbar_wait<true>(&a_free[land], lphase ^ 1);
+                        if (hf == 0) TL(gp, 0);
+                        mbar_expect_tx(&full_a[land], A_TILE_BYTES);
+                        tma_load_4d(landing(land), &p.tmA[map], &full_a[land], c0 + 32 * hf, wo0 + dx, ho0 + dy, img);
+                        if (++land == C::LANDINGS) { land = 0; lphase ^= 1; }
+                    }
                     mbar_wait<true>(&empty[stage], phase ^ 1);
                     mbar_expect_tx(&full_b[stage], ((p.ablate & 1) ? 1 : 2) * C::B_TILE_BYTES);
                     tma_load_2d(stage_b_hi(stage), &p.tmBhi, &full_b[stage], kcol, n_tile * BN);
@@ -301,7 +349,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     if (++cc == cchunks) { cc = 0; ++tap; if (++sx == p.KW) { sx = 0; ++r; } }
                     TL(gp, 1); ++gp;
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
-                    if (++land == C::LANDINGS) { land = 0; lphase ^= 1; }
                 }
             }
         }
@@ -309,8 +356,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         // ============================================================== MMA issuers (warps 1, 14, 15: K-blocks round-robin)
         const uint32_t me = warp == 1 ? 0u : (uint32_t)(warp - 13);
         if (lane == 0 && me < (uint32_t)C::ISSUERS) {
-            // instruction descriptor: D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10), both K-major, N>>3 at bit 17, M>>4 at bit 24
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+            // instruction descriptor: D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10) | F16 (0, 0), both K-major, N>>3 at bit 17, M>>4 at bit 24
+            const uint32_t idesc = (1u << 4) | (MODE ? 0u : ((2u << 7) | (2u << 10))) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+            auto mma = [&](uint32_t d, uint32_t a, uint64_t b, uint32_t acc) {
+                if constexpr (MODE) umma_f16_ts(d, a, b, idesc, acc); else umma_tf32_ts(d, a, b, idesc, acc);
+            };
             // Issuing a tcgen05.mma blocks the thread for about its execution time, and every barrier wait costs a few
             // hundred cycles; with a single issuer the tensor pipe idled ~40% of each K-block.  ISSUERS threads take
             // K-blocks round-robin, so one thread's waits overlap the others' MMAs.  Issuer i owns partial-sum buffer i.
@@ -318,7 +368,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             uint32_t turn = 0, mine = 0;                                      // g % ISSUERS; K-blocks this thread has issued
             int stage = 0; uint32_t phase = 0;
             const uint32_t buf = me;
+            const bool a_exact = p.a_exact != 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                int cc = 0;
                 for (int kb = 0; kb < kblocks; ++kb, ++g) {
                     if (turn == me) {
                         // operands first (normally long complete), the partial-sum buffer last: its release by the drain
@@ -332,15 +384,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                         const uint32_t d_tmem = tmem_base + buf * BN;
                         const uint32_t a_hi = tmem_base + C::TMEM_A0 + stage * 64, a_lo = a_hi + 32;   // A operand: tensor memory
                         const uint64_t b_hi = umma_desc(smem_u32(stage_b_hi(stage))), b_lo = umma_desc(smem_u32(stage_b_lo(stage)));
-                        // one K-step = 8 tf32: +8 TMEM columns for A, +32 bytes (+2 in the addr>>4 field) inside B's swizzle span.
+                        // one K-step = 8 tf32 | 16 fp16: +8 TMEM columns for A, +32 bytes (+2 in the addr>>4 field) inside B's
+                        // swizzle span.  MODE 1: a K-block that starts within 32 channels of Cin only has 2 K-steps.
                         // Small terms first: while the accumulator is tiny its round-toward-zero losses are negligible.
+                        const int ksteps = (MODE && cc * C::KBLK + 32 >= p.Cin) ? 2 : 4;
+                        if (!a_exact) {
 #pragma unroll
-                        for (int k = 0; k < KB / 8; ++k) {
-                            umma_tf32_ts(d_tmem, a_lo + 8 * k, b_hi + 2 * k, idesc, k != 0);
-                            umma_tf32_ts(d_tmem, a_hi + 8 * k, b_lo + 2 * k, idesc, 1);
+                            for (int k = 0; k < 4; ++k) {
+                                if (k < ksteps) {
+                                    mma(d_tmem, a_lo + 8 * k, b_hi + 2 * k, k != 0);
+                                    mma(d_tmem, a_hi + 8 * k, b_lo + 2 * k, 1);
+                                }
+                            }
+                        } else {                                              // a_lo == 0 (integer-valued activations)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if (k < ksteps) mma(d_tmem, a_hi + 8 * k, b_lo + 2 * k, k != 0);
                         }
 #pragma unroll
-                        for (int k = 0; k < KB / 8; ++k) umma_tf32_ts(d_tmem, a_hi + 8 * k, b_hi + 2 * k, idesc, 1);
+                        for (int k = 0; k < 4; ++k)
+                            if (k < ksteps) mma(d_tmem, a_hi + 8 * k, b_hi + 2 * k, 1);
                         umma_commit(&empty[stage]);                           // smem slot + TMEM A slot reusable once these MMAs retire
                         umma_commit(&d_full[buf]);                            // partial sum of this K-block complete
                         TL(g, 4);
@@ -348,6 +411,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     }
                     if (++turn == (uint32_t)C::ISSUERS) turn = 0;
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    if (++cc == cchunks) cc = 0;
                 }
             }
         }
@@ -357,32 +421,95 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-        int stage = 0, land = 0; uint32_t phase = 0, lphase = 0; uint32_t gc = 0; (void)gc;
+        int stage = 0, land = 0; uint32_t phase = 0, lphase = 0; uint32_t gc = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            int cc = 0;
             for (int kb = 0; kb < kblocks; ++kb) {
-                mbar_wait<true>(&full_a[land], lphase);
-                if (warp == 2 && lane == 0) TL(gc, 5);
-                const uint32_t src = smem_u32(landing(land)) + row * 128;
-                uint4 v[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) v[c] = lds128(src + (uint32_t)((c ^ (row & 7)) << 4));   // undo the 128B swizzle: logical chunk c
-                uint32_t hi[32], lo[32];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const uint32_t w[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        hi[4 * c + e] = w[e] & 0xFFFFE000u;
-                        lo[4 * c + e] = __float_as_uint(__uint_as_float(w[e]) - __uint_as_float(hi[4 * c + e])) & 0xFFFFE000u;
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&a_free[land]);                    // the landing buffer is in registers: refill it
-                mbar_wait<true>(&empty[stage], phase ^ 1);                    // the stage's TMEM slot: MMAs of K-block g - STAGES retired
-                tc_fence_after();
                 const uint32_t dst = tmem_base + C::TMEM_A0 + stage * 64 + lane_addr;
-                tmem_st32(dst, hi);
-                tmem_st32(dst + 32, lo);
+                if constexpr (MODE == 0) {
+                    mbar_wait<true>(&full_a[land], lphase);
+                    if (warp == 2 && lane == 0) TL(gc, 5);
+                    const uint32_t src = smem_u32(landing(land)) + row * 128;
+                    uint4 v[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) v[c] = lds128(src + (uint32_t)((c ^ (row & 7)) << 4));   // undo the 128B swizzle: logical chunk c
+                    uint32_t hi[32], lo[32];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const uint32_t w[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            hi[4 * c + e] = w[e] & 0xFFFFE000u;
+                            lo[4 * c + e] = __float_as_uint(__uint_as_float(w[e]) - __uint_as_float(hi[4 * c + e])) & 0xFFFFE000u;
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&a_free[land]);                // the landing buffer is in registers: refill it
+                    if (++land == C::LANDINGS) { land = 0; lphase ^= 1; }
+                    mbar_wait<true>(&empty[stage], phase ^ 1);                // the stage's TMEM slot: MMAs of K-block g - STAGES retired
+                    tc_fence_after();
+                    tmem_st32(dst, hi);
+                    tmem_st32(dst + 32, lo);
+                } else {
+                    // ---- block-scaled fp16 split of this thread's pixel row (64 channels, or 32 in a trailing half block)
+                    const bool two = cc * C::KBLK + 32 < p.Cin;
+                    float x[64];
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        if (hf == 0 || two) {
+                            mbar_wait<true>(&full_a[land], lphase);
+                            if (hf == 0 && warp == 2 && lane == 0) TL(gc, 5);
+                            const uint32_t src = smem_u32(landing(land)) + row * 128;
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                const uint4 q = lds128(src + (uint32_t)((c ^ (row & 7)) << 4));           // logical 16-byte chunk c
+                                x[32 * hf + 4 * c] = __uint_as_float(q.x); x[32 * hf + 4 * c + 1] = __uint_as_float(q.y);
+                                x[32 * hf + 4 * c + 2] = __uint_as_float(q.z); x[32 * hf + 4 * c + 3] = __uint_as_float(q.w);
+                            }
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&a_free[land]);        // the landing unit is in registers: refill it
+                            if (++land == C::LANDINGS) { land = 0; lphase ^= 1; }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) x[32 + j] = 0.f;
+                        }
+                    }
+                    // row maximum -> power-of-two scale that puts it into [2^14, 2^15) (fp16 max 65504); rows of zeros and
+                    // magnitudes below 2^-63 use the scale of 2^-63 (their contribution is below fp32 resolution anyway)
+                    float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 64; j += 4) {
+                        m0 = fmaxf(m0, fabsf(x[j])); m1 = fmaxf(m1, fabsf(x[j + 1]));
+                        m2 = fmaxf(m2, fabsf(x[j + 2])); m3 = fmaxf(m3, fabsf(x[j + 3]));
+                    }
+                    const uint32_t mbits = __float_as_uint(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+                    int e = (int)(mbits >> 23);                               // biased exponent of the row maximum (<= 254 for finite data)
+                    e = e < 64 ? 64 : (e > 254 ? 254 : e);
+                    const float sc = __uint_as_float((uint32_t)(268 - e) << 23);             // 2^(14 - (e - 127))
+                    int ie = e - 14 - p.w_exp;                                               // 1 / (sc * 2^w_exp)
+                    ie = ie < 1 ? 1 : (ie > 254 ? 254 : ie);
+                    mbar_wait<true>(&empty[stage], phase ^ 1);                // the stage's TMEM slot: MMAs of K-block g - STAGES retired
+                    tc_fence_after();
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        if (hf == 0 || two) {
+                            uint32_t hi[16], lo[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const float a0 = x[32 * hf + 2 * j] * sc, a1 = x[32 * hf + 2 * j + 1] * sc;
+                                const __half2 h = __floats2half2_rn(a0, a1);  // low half = even channel (the K order of a TMEM column)
+                                const float2 hf2 = __half22float2(h);
+                                const __half2 l = __floats2half2_rn(a0 - hf2.x, a1 - hf2.y);
+                                hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+                                lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+                            }
+                            tmem_st16(dst + 16 * hf, hi);
+                            tmem_st16(dst + 32 + 16 * hf, lo);
+                        }
+                    }
+                    tmem_st1(tmem_base + C::TMEM_SC0 + (gc & (C::SCALE_SLOTS - 1)) + lane_addr, (uint32_t)ie << 23);
+                    if (++cc == cchunks) cc = 0;
+                }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 __syncwarp();
@@ -390,7 +517,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 if (warp == 2 && lane == 0) TL(gc, 6);
                 ++gc;
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
-                if (++land == C::LANDINGS) { land = 0; lphase ^= 1; }
             }
         }
     } else if (warp < 14) {
@@ -497,13 +623,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 {
                     const uint32_t src = tmem_base + buf * BN + lane_col;
                     uint32_t va[16], vb[16];
+                    uint32_t scale_bits = 0x3F800000u;
+                    if constexpr (MODE) tmem_ld1_issue(tmem_base + C::TMEM_SC0 + (g & (C::SCALE_SLOTS - 1)) + ((uint32_t)(quarter * 32) << 16), scale_bits);
                     tmem_ld16_issue(src, va);
                     tmem_ld_wait();
+                    // MODE 1: partial * 2^-k (exact) added with one rounding - the fma is the TF32 mode's add
+                    const float inv = __uint_as_float(scale_bits);
+                    auto accum = [&](float& a, uint32_t v) {
+                        if constexpr (MODE) a = fmaf(__uint_as_float(v), inv, a); else a += __uint_as_float(v);
+                    };
 #pragma unroll
                     for (int pc = 0; pc < HALF / 16; pc += 2) {
                         if (pc + 1 < HALF / 16) tmem_ld16_issue(src + (pc + 1) * 16, vb);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) acc[pc * 16 + j] += __uint_as_float(va[j]);   // round-to-nearest fp32 running sum
+                        for (int j = 0; j < 16; ++j) accum(acc[pc * 16 + j], va[j]);                 // round-to-nearest fp32 running sum
                         if (pc + 1 < HALF / 16) {
                             tmem_ld_wait();
                             if (pc + 2 < HALF / 16) tmem_ld16_issue(src + (pc + 2) * 16, va);
@@ -513,7 +646,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                                 if (lane == 0) mbar_arrive(&d_empty[buf]);
                             }
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) acc[(pc + 1) * 16 + j] += __uint_as_float(vb[j]);
+                            for (int j = 0; j < 16; ++j) accum(acc[(pc + 1) * 16 + j], vb[j]);
                             if (pc + 2 < HALF / 16) tmem_ld_wait();
                         }
                     }
@@ -648,24 +781,25 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-bool make_map(CUtensorMap* map, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+bool make_map(CUtensorMap* map, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box,
+              CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT32) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, base, dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    return fn(map, dtype, rank, base, dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN>
+template <int BN, int MODE>
 int launch(fcp_ctx* ctx, const TcParams& p) {
-    using C = Cfg<BN>;
-    static bool configured = false;
-    if (!configured) {
-        FCP_CUDA(ctx, cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        configured = true;
+    using C = Cfg<BN, MODE>;
+    static uint64_t configured = 0;                    // one bit per device: the attribute is per device
+    if (!((configured >> (ctx->device & 63)) & 1)) {
+        FCP_CUDA(ctx, (cudaFuncSetAttribute(conv_tc_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES)));
+        configured |= (uint64_t)1 << (ctx->device & 63);
     }
     int grid = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
-    conv_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, ctx->stream>>>(p);
+    conv_tc_kernel<BN, MODE><<<grid, NUM_THREADS, C::SMEM_BYTES, ctx->stream>>>(p);
     FCP_KERNEL_CHECK(ctx);
     return FCP_OK;
 }
@@ -728,11 +862,18 @@ int launch_conv_tc(fcp_ctx* ctx, const ConvOp& op) {
             if (!make_map(&p.tmA[py * 2 + px], base + ((size_t)py * W + px) * cs, 4, dims, strides, box))
                 return fail(ctx, FCP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the activation tensor");
         }
-    const cuuint64_t K = (cuuint64_t)p.KH * p.KW * wt.cin;
+    const bool f16 = op.impl == 2;
+    if (f16 && !wt.h_hi) return fail(ctx, FCP_ERR_INVALID, "conv_tc: this convolution has no fp16 packing");
+    p.cin_p = f16 ? wt.cin_p : wt.cin;
+    p.w_exp = wt.w_exp;
+    p.a_exact = op.a_exact;
+    const cuuint64_t K = (cuuint64_t)p.KH * p.KW * p.cin_p;
     cuuint64_t bdims[2] = {K, (cuuint64_t)wt.cout_pad};
-    cuuint64_t bstr[1] = {K * 4};
-    cuuint32_t bbox[2] = {KB, (cuuint32_t)BN};
-    if (!make_map(&p.tmBhi, wt.w_hi, 2, bdims, bstr, bbox) || !make_map(&p.tmBlo, wt.w_lo, 2, bdims, bstr, bbox))
+    cuuint64_t bstr[1] = {K * (f16 ? 2 : 4)};
+    cuuint32_t bbox[2] = {(cuuint32_t)(f16 ? 64 : 32), (cuuint32_t)BN};
+    const CUtensorMapDataType bt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    if (!make_map(&p.tmBhi, f16 ? wt.h_hi : (void*)wt.w_hi, 2, bdims, bstr, bbox, bt) ||
+        !make_map(&p.tmBlo, f16 ? wt.h_lo : (void*)wt.w_lo, 2, bdims, bstr, bbox, bt))
         return fail(ctx, FCP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the weights");
     // ---- epilogue tensor maps: one box = the tile's 128 pixels x 32 channels (one chunk of an epilogue group)
     {
@@ -762,9 +903,14 @@ int launch_conv_tc(fcp_ctx* ctx, const ConvOp& op) {
     static const int ablate = getenv("FCP_TC_ABLATE") ? atoi(getenv("FCP_TC_ABLATE")) : 0;
     p.ablate = ablate;
     auto do_launch = [&]() -> int {
-        if (BN == 128) return launch<128>(ctx, p);
-        if (BN == 64) return launch<64>(ctx, p);
-        return launch<32>(ctx, p);
+        if (f16) {
+            if (BN == 128) return launch<128, 1>(ctx, p);
+            if (BN == 64) return launch<64, 1>(ctx, p);
+            return launch<32, 1>(ctx, p);
+        }
+        if (BN == 128) return launch<128, 0>(ctx, p);
+        if (BN == 64) return launch<64, 0>(ctx, p);
+        return launch<32, 0>(ctx, p);
     };
 #ifdef FCP_EXP_TIMELINE
     // clock64 stamps of CTA 0 for one launch of the shape FCP_TL_SHAPE="k,cin,cout" (default 3,256,256), K-blocks
@@ -787,7 +933,7 @@ int launch_conv_tc(fcp_ctx* ctx, const ConvOp& op) {
         cudaMemcpy(h.data(), dbg, 512 * 16 * 8, cudaMemcpyDeviceToHost);
         long long t0 = h[g0 * 16 + 0];
         fprintf(stderr, "[timeline] k%d cin%d cout%d BN=%d res=%d kblocks/tile=%d tiles=%d\n", tk, tcin, tcout, BN, (int)(op.res1 || op.res2),
-                wt.k * wt.k * wt.cin / KB, p.num_tiles);
+                p.KH * p.KW * ((wt.cin + (f16 ? 63 : 31)) / (f16 ? 64 : 32)), p.num_tiles);
         fprintf(stderr, "[timeline] g: prod_wait_empty prod_issued | mma_dempty mma_conv mma_issued | conv_full conv_done | drain_dfull drain_done | epi_done res_landed phase1_done om_done | tile_prologue_done\n");
         for (int g = g0; g < g0 + gn && g < 512; ++g) {
             fprintf(stderr, "[timeline] %3d:", g);

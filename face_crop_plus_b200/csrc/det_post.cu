@@ -329,10 +329,10 @@ int launch_det_post(fcp_ctx* ctx, const float* const* level_ptrs, const float* h
     det_decode_kernel<<<grid, 256, 0, ctx->stream>>>(s, n, h, w, vis_thr, rec, keys, key_cap, cand_count);
     FCP_KERNEL_CHECK(ctx);
     const size_t nms_smem = (size_t)NMS_SMEM_KEYS * (sizeof(float4) + sizeof(unsigned long long) + 1);
-    static bool configured = false;
-    if (!configured) {
+    static uint64_t configured = 0;                    // one bit per device: the attribute is per device
+    if (!((configured >> (ctx->device & 63)) & 1)) {
         FCP_CUDA(ctx, cudaFuncSetAttribute(det_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem));
-        configured = true;
+        configured |= (uint64_t)1 << (ctx->device & 63);
     }
     det_nms_kernel<<<n, NMS_THREADS, nms_smem, ctx->stream>>>(rec, keys, key_cap, cand_count, s.A, nms_thr, strategy, supp, kept_count);
     FCP_KERNEL_CHECK(ctx);

@@ -50,7 +50,7 @@ bool Exec::conv(const std::string& name, Tensor in, Tensor out, int stride, int 
     ConvOp op = extra;
     op.in = in; op.out = out; op.wt = wt; op.stride = stride; op.pad = pad; op.act = act;
     op.impl = ctx->use_tc;
-    if (op.up_in && op.impl == 1 && in.c % 32 == 0) {
+    if (op.up_in && op.impl >= 1 && in.c % 32 == 0) {
         // the tensor-core kernel needs a dense input for its TMA boxes: materialise the nearest x2 upsample (HBM-bound copy)
         Tensor up = alloc(in.n, in.h * 2, in.w * 2, in.c);
         if (!ok()) return false;
@@ -83,6 +83,7 @@ static void stem7(Exec& ex, const std::string& name, const void* src, int mode, 
     if (ex.ok() && !ex.dry) ex.status = launch_stem_rows(ex.ctx, src, mode, nb, h, w, rows);
     ConvOp e;
     e.stride_w = 1; e.pad_w = 0;
+    e.a_exact = mode == 0;      // u8 minus an integer mean: 9 significant bits, the split's low part is exactly zero
     ex.conv(name + ".rows", rows, out, 2, 3, FCP_ACT_RELU, e);
     ex.free(rows);
 }

@@ -299,11 +299,11 @@ int launch_stem7(fcp_ctx* ctx, const void* src, int mode, int n, int h, int w, c
                  const float* shift, Tensor out) {
     // weights + 3 channel planes + raw row staging (mode 1 rows are floats: ST_PW*3 words)
     size_t smem = (147 * 64 + 3 * ST_PH * ST_LD + ST_PH * (ST_PW * 3 + 3)) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    static uint64_t configured = 0;                    // one bit per device: the attribute is per device
+    if (!((configured >> (ctx->device & 63)) & 1)) {
         FCP_CUDA(ctx, cudaFuncSetAttribute(stem7_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         FCP_CUDA(ctx, cudaFuncSetAttribute(stem7_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured |= (uint64_t)1 << (ctx->device & 63);
     }
     dim3 grid((out.w + ST_TW - 1) / ST_TW, (out.h + ST_TH - 1) / ST_TH, n);
     if (mode == 0)

@@ -4,6 +4,8 @@
 #include <cstdio>
 #include <cstring>
 
+#include <cuda_fp16.h>
+
 #include "common.h"
 #include "graphs.h"
 
@@ -108,6 +110,36 @@ static inline float tf32_trunc(float x) {
     return r;
 }
 
+// f16x3 packing of a K-major fp32 matrix wk[cout_pad][taps][cin] (BN scale already folded in): one power-of-two scale per
+// layer puts max |w| into [2^13, 2^14); hi = rn_f16(w * 2^e), lo = rn_f16(w * 2^e - hi); each tap is padded to a multiple
+// of 64 channels (one K-block of the kernel) with zeros.
+static int pack_f16(fcp_ctx* ctx, ConvWeights& cw, const std::vector<float>& wk, int taps, int cin) {
+    float wmax = 0.f;
+    for (float v : wk) wmax = std::max(wmax, std::fabs(v));
+    int ew = 0;
+    if (wmax > 0.f && std::isfinite(wmax)) std::frexp(wmax, &ew);        // wmax = m * 2^ew, 0.5 <= m < 1
+    cw.w_exp = std::min(40, std::max(-40, 14 - ew));                     // wmax * 2^w_exp in [2^13, 2^14)
+    cw.cin_p = (cin + 63) / 64 * 64;
+    const size_t Kp = (size_t)taps * cw.cin_p;
+    std::vector<__half> hi((size_t)cw.cout_pad * Kp, __float2half_rn(0.f)), lo(hi);
+    const float sc = std::ldexp(1.0f, cw.w_exp);
+    for (int o = 0; o < cw.cout_pad; ++o)
+        for (int t = 0; t < taps; ++t)
+            for (int c = 0; c < cin; ++c) {
+                const float v = wk[((size_t)o * taps + t) * cin + c] * sc;
+                const __half h = __float2half_rn(v);
+                hi[(size_t)o * Kp + (size_t)t * cw.cin_p + c] = h;
+                lo[(size_t)o * Kp + (size_t)t * cw.cin_p + c] = __float2half_rn(v - __half2float(h));
+            }
+    for (auto* pp : {&cw.h_hi, &cw.h_lo}) {
+        FCP_CUDA(ctx, cudaMalloc(pp, hi.size() * sizeof(__half)));
+        ctx->device_allocs.push_back(*pp);
+    }
+    FCP_CUDA(ctx, cudaMemcpy(cw.h_hi, hi.data(), hi.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    FCP_CUDA(ctx, cudaMemcpy(cw.h_lo, lo.data(), lo.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    return FCP_OK;
+}
+
 // Packs conv `convs[i].weight` (OIHW, concatenated along Cout) with optional bias and optional BatchNorm `bn`
 // (running stats folded like ATen's eval batch_norm: alpha = gamma/sqrt(var+eps), beta = bias - mean*alpha).
 int pack_conv(fcp_ctx* ctx, Model& m, const std::vector<std::string>& convs, const std::string& bn,
@@ -158,7 +190,7 @@ int pack_conv(fcp_ctx* ctx, Model& m, const std::vector<std::string>& convs, con
     // K-major [cout_pad][K] with the per-channel SCALE FOLDED IN (w*scale, then split into tf32 hi + lo), so that its
     // epilogue only adds the shift - done while the K loop still runs, off the tile-boundary critical path.
     std::vector<float> wkn((size_t)K * cw.cout_pad, 0.f);
-    std::vector<float> whi((size_t)cw.cout_pad * K, 0.f), wlo((size_t)cw.cout_pad * K, 0.f);
+    std::vector<float> whi((size_t)cw.cout_pad * K, 0.f), wlo((size_t)cw.cout_pad * K, 0.f), wfull((size_t)cw.cout_pad * K, 0.f);
     int o0 = 0;
     for (size_t g = 0; g < ws.size(); ++g) {
         const HostTensor& w = *ws[g];
@@ -172,6 +204,7 @@ int pack_conv(fcp_ctx* ctx, Model& m, const std::vector<std::string>& convs, con
                         wkn[kk * cw.cout_pad + o0 + o] = v;
                         const float vs = v * scale[o0 + o];
                         float hi = tf32_trunc(vs);
+                        wfull[(size_t)(o0 + o) * K + kk] = vs;
                         whi[(size_t)(o0 + o) * K + kk] = hi;
                         wlo[(size_t)(o0 + o) * K + kk] = tf32_trunc(vs - hi);
                     }
@@ -180,6 +213,7 @@ int pack_conv(fcp_ctx* ctx, Model& m, const std::vector<std::string>& convs, con
     FCP_TRY(upload(ctx, wkn, &cw.w_kn));
     FCP_TRY(upload(ctx, whi, &cw.w_hi));
     FCP_TRY(upload(ctx, wlo, &cw.w_lo));
+    if (cw.cin % 32 == 0) FCP_TRY(pack_f16(ctx, cw, wfull, cw.k * cw.k, cw.cin));
     FCP_TRY(upload(ctx, scale, &cw.scale));
     FCP_TRY(upload(ctx, shift, &cw.shift));
     m.conv[name] = cw;
@@ -198,7 +232,7 @@ int pack_stem_rows(fcp_ctx* ctx, Model& m, const std::string& conv, const std::s
     cw.cin = 32; cw.k = 7; cw.kh = 7; cw.kw = 1; cw.alg_k = 147;
     cw.w_kn = nullptr;                                 // no CUDA-core packing: this route exists on the tensor cores only
     const int K = 7 * 32;
-    std::vector<float> whi((size_t)cw.cout_pad * K, 0.f), wlo((size_t)cw.cout_pad * K, 0.f);
+    std::vector<float> whi((size_t)cw.cout_pad * K, 0.f), wlo((size_t)cw.cout_pad * K, 0.f), wfull((size_t)cw.cout_pad * K, 0.f);
     for (int o = 0; o < cw.cout; ++o)
         for (int c = 0; c < 3; ++c)
             for (int r = 0; r < 7; ++r)
@@ -206,11 +240,13 @@ int pack_stem_rows(fcp_ctx* ctx, Model& m, const std::string& conv, const std::s
                     const float v = w->data[(((size_t)o * 3 + c) * 7 + r) * 7 + sx] * scale[o];   // folded BN scale, like pack_conv
                     const size_t kk = (size_t)r * 32 + sx * 3 + c;
                     const float hi = tf32_trunc(v);
+                    wfull[(size_t)o * K + kk] = v;
                     whi[(size_t)o * K + kk] = hi;
                     wlo[(size_t)o * K + kk] = tf32_trunc(v - hi);
                 }
     FCP_TRY(upload(ctx, whi, &cw.w_hi));
     FCP_TRY(upload(ctx, wlo, &cw.w_lo));
+    FCP_TRY(pack_f16(ctx, cw, wfull, 7, 32));
     m.conv[name] = cw;
     return FCP_OK;
 }
@@ -260,7 +296,7 @@ DevOut::~DevOut() {
 }
 
 int run_conv(fcp_ctx* ctx, const ConvOp& op) {
-    const bool tc = op.impl == 1 && conv_tc_supported(op);   // shapes the tensor-core kernel does not cover use the CUDA-core kernel
+    const bool tc = op.impl >= 1 && conv_tc_supported(op);   // shapes the tensor-core kernel does not cover use the CUDA-core kernel
     if (!tc && !op.wt->w_kn) return fail(ctx, FCP_ERR_INVALID, "conv: this packing exists for the tensor-core kernel only");
     if (!ctx->profile) return tc ? launch_conv_tc(ctx, op) : launch_conv_ffma(ctx, op);
     if (ctx->prof_used + 2 > ctx->prof_events.size()) {
@@ -358,7 +394,7 @@ int fcp_set_micro_batch(fcp_ctx* ctx, int detect_images, int parse_faces) {
 }
 
 int fcp_set_conv_impl(fcp_ctx* ctx, int impl) {
-    if (!ctx || impl < 0 || impl > 1) return fail(ctx, FCP_ERR_INVALID, "conv impl must be 0 or 1");
+    if (!ctx || impl < 0 || impl > 2) return fail(ctx, FCP_ERR_INVALID, "conv impl must be 0, 1 or 2");
     ctx->use_tc = impl;
     return FCP_OK;
 }

@@ -51,6 +51,7 @@ def parse_landmarks_file(file_path: str, **kwargs) -> tuple[np.ndarray, np.ndarr
     else:
         if file_path.endswith(".csv"):
             kwargs.setdefault("delimiter", ",")
+            kwargs.setdefault("skip_header", 1)          # utils.py:70-71: a .csv carries a header row
         names = np.genfromtxt(file_path, usecols=0, dtype=str, **kwargs)
         lms = np.genfromtxt(file_path, dtype=np.float32, **kwargs)[:, 1:]
     return lms.reshape(len(lms), -1, 2), names

@@ -55,7 +55,8 @@ int fcp_sync(fcp_ctx* ctx);
 int64_t fcp_launch_count(const fcp_ctx* ctx);
 /* images per detector micro-batch / faces per parser micro-batch (bounds the activation arena; default 16 / 32) */
 int fcp_set_micro_batch(fcp_ctx* ctx, int detect_images, int parse_faces);
-/* convolution kernel used by the model graphs: 1 = tcgen05 3xTF32 (default), 0 = CUDA-core fp32; both are fp32-accurate.
+/* convolution kernel used by the model graphs: 2 = tcgen05 3xFP16 block-scaled split (default), 1 = tcgen05 3xTF32 split,
+ * 0 = CUDA-core fp32; all three are fp32-accurate (error vs fp64 <= that of an fp32 FMA chain; tests/test_gpu_parity.py).
  * The environment variable FCP_CONV_IMPL sets the default of new contexts. */
 int fcp_set_conv_impl(fcp_ctx* ctx, int impl);
 
@@ -163,7 +164,7 @@ int fcp_pipeline(fcp_ctx* ctx, const uint8_t* images, int n, int h, int w, const
 /* ---- kernel-level test hook: one fused convolution (what nn.Conv2d + BatchNorm2d + activation do in the
  * reference graphs).  x f32 NHWC [n,h,w,cin]; weight f32 OIHW host [cout,cin,k,k]; scale/shift f32 [cout] host
  * (NULL = 1/0); residual f32 NHWC [n,ho,wo,cout] added before the activation (NULL = none);
- * out f32 NHWC [n,ho,wo,cout].  impl: 0 = CUDA-core fp32 kernel, 1 = tcgen05 3xTF32 kernel. */
+ * out f32 NHWC [n,ho,wo,cout].  impl: 0 = CUDA-core fp32 kernel, 1 = tcgen05 3xTF32 kernel, 2 = tcgen05 3xFP16 block-scaled kernel. */
 int fcp_conv2d(fcp_ctx* ctx, const float* x, int n, int h, int w, int cin, const float* weight, int cout, int k,
                int stride, int pad, const float* scale, const float* shift, const float* residual, int act,
                float slope, int impl, float* out);

@@ -63,11 +63,13 @@ CONV_CASES = [  # (n, h, w, cin, cout, k, stride, pad, act, residual)
     (4, 64, 64, 64, 256, 1, 1, 0, "relu", True),      # 256 tiles > 148 CTAs: slab / residual reuse across a CTA's tiles
     (2, 30, 50, 64, 48, 3, 1, 1, "relu", True),       # Cout = 32 + 16: second TMA chunk clipped, residual zero-filled
     (1, 96, 96, 32, 160, 3, 2, 1, "lrelu", False),    # general epilogue form, stride-2 parity views, cout_pad 160 -> BN 32
+    (1, 24, 40, 160, 32, 3, 1, 1, "lrelu", False),    # f16x3: 2.5 K-blocks per tap (trailing 32-channel half block)
+    (2, 48, 48, 128, 128, 3, 1, 1, "relu", False),    # BN = 128, 18 K-blocks of 64 channels
 ]
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1, 2])
 def test_conv2d_matches_torch(ctx, case, impl):
     n, h, w, cin, cout, k, stride, pad, act, use_res = case
     g = torch.Generator().manual_seed(hash(case) & 0xFFFF)
@@ -88,7 +90,8 @@ def test_conv2d_matches_torch(ctx, case, impl):
 
 
 def test_conv2d_tensor_core_accuracy_large_k(ctx):
-    """3xTF32 on tcgen05 must be as accurate as the fp32 CUDA-core kernel (K = 9*512 = 4608, fp64 reference)."""
+    """Both tensor-core split schemes (3xTF32, block-scaled 3xFP16) must be as accurate as the fp32 CUDA-core kernel
+    (K = 9*512 = 4608, fp64 reference)."""
     g = torch.Generator().manual_seed(7)
     n, h, w, cin, cout = 2, 32, 32, 512, 256
     x = torch.randn((n, cin, h, w), generator=g).abs() + 0.5           # all-positive inputs: worst case for biased rounding
@@ -96,11 +99,39 @@ def test_conv2d_tensor_core_accuracy_large_k(ctx):
     ref = torch.nn.functional.conv2d(x.double(), wt.double(), None, 1, 1).permute(0, 2, 3, 1).numpy()
     xin = x.permute(0, 2, 3, 1).contiguous().numpy()
     err = {}
-    for impl in (0, 1):
+    for impl in (0, 1, 2):
         got = ctx.conv2d(xin, wt.numpy(), 1, 1, impl=impl)
         err[impl] = np.abs(got - ref).max() / np.abs(ref).max()
-    print("relative max error  cuda-core fp32: %.3e   tcgen05 3xTF32: %.3e" % (err[0], err[1]))
+    print("relative max error  cuda-core fp32: %.3e   tcgen05 3xTF32: %.3e   tcgen05 3xFP16 block-scaled: %.3e" % (err[0], err[1], err[2]))
     assert err[1] < 5e-6 and err[1] < 8 * max(err[0], 1e-7)
+    assert err[2] < 5e-6 and err[2] < 8 * max(err[0], 1e-7)
+
+
+def test_conv2d_f16x3_dynamic_range(ctx):
+    """The block scaling of the 3xFP16 mode: pixel rows spanning 2^-40 .. 2^40 (far outside fp16's 2^-24 .. 2^16), output
+    channels whose weights span 2^-12 .. 1, exact zeros, and rows of zeros.  Error is measured per output element against
+    sum |a||w| (the scale of its rounding noise) and must stay at the fp32 level everywhere - and not exceed the fp32
+    CUDA-core kernel's."""
+    g = torch.Generator().manual_seed(11)
+    n, h, w, cin, cout = 1, 32, 32, 192, 64
+    x = torch.randn((n, cin, h, w), generator=g)
+    row_exp = torch.randint(-40, 41, (n, 1, h, w), generator=g).float()
+    x = x * torch.exp2(row_exp)
+    x[:, :, 3, :] = 0.0                                                  # rows of zeros
+    x[:, ::7] = 0.0                                                      # exact zeros inside every row
+    x[:, 5:9] *= 2.0 ** -14                                              # channels far below their row maximum
+    wt = torch.randn((cout, cin, 3, 3), generator=g) * 0.05
+    wt = wt * torch.exp2(-torch.randint(0, 13, (cout, 1, 1, 1), generator=g).float())
+    ref = torch.nn.functional.conv2d(x.double(), wt.double(), None, 1, 1).permute(0, 2, 3, 1).numpy()
+    den = torch.nn.functional.conv2d(x.double().abs(), wt.double().abs(), None, 1, 1).permute(0, 2, 3, 1).numpy()
+    xin = x.permute(0, 2, 3, 1).contiguous().numpy()
+    err = {}
+    for impl in (0, 1, 2):
+        got = ctx.conv2d(xin, wt.numpy(), 1, 1, impl=impl)
+        assert np.isfinite(got).all()
+        err[impl] = float(np.max(np.abs(got - ref) / np.maximum(den, 1e-300)))
+    print("max |err| / sum|a||w|   cuda-core fp32: %.3e   3xTF32: %.3e   3xFP16 block-scaled: %.3e" % (err[0], err[1], err[2]))
+    assert err[2] < 4e-7 and err[2] <= 2 * max(err[0], err[1])
 
 
 # ---------------------------------------------------------------------------------------------------------- align
@@ -352,19 +383,20 @@ def test_detect_full_size_vs_oracle(ctx):
 
 
 def test_full_size_batch_consistency_between_conv_kernels(det_ctx, par_ctx):
-    """Size-independent property at the bench shape (1024x1024, 24 images, ragged micro-batches): the tensor-core
-    (3xTF32) and the CUDA-core (fp32) convolution paths must select the same priors and agree to the float tolerance."""
+    """Size-independent property at the bench shape (1024x1024, 24 images, ragged micro-batches): the two tensor-core
+    paths (3xFP16 block-scaled, 3xTF32) and the CUDA-core (fp32) convolution path must select the same priors and agree
+    to the float tolerance."""
     imgs = synth.make_images(24, 1024, 1024, seed=4000)
     tgt = landmarks_target((256, 256), 0.65)
     res = {}
-    for impl in (1, 0):
+    for impl in (2, 1, 0):
         det_ctx.set_conv_impl(impl)
         det_ctx.set_micro_batch(16 if impl else 5, 32 if impl else 7)
         res[impl] = det_ctx.pipeline(imgs, None, tgt, (256, 256), 0.6, 0.4, "largest")
-    det_ctx.set_conv_impl(1)
+    det_ctx.set_conv_impl(2)
     det_ctx.set_micro_batch(16, 32)
-    a, b = res[1], res[0]
-    assert a["count"] == b["count"] > 0 and a["indices"].tolist() == b["indices"].tolist()
-    assert np.abs(a["landmarks"] - b["landmarks"]).max() < TOL
-    assert (a["crops"] != b["crops"]).mean() < 0.02 and (a["labels"] != b["labels"]).mean() < 5e-3
-    assert np.array_equal(a["hist"].sum(1), np.full(a["count"], 256 * 256))
+    for a, b in ((res[2], res[0]), (res[1], res[0]), (res[2], res[1])):
+        assert a["count"] == b["count"] > 0 and a["indices"].tolist() == b["indices"].tolist()
+        assert np.abs(a["landmarks"] - b["landmarks"]).max() < TOL
+        assert (a["crops"] != b["crops"]).mean() < 0.02 and (a["labels"] != b["labels"]).mean() < 5e-3
+        assert np.array_equal(a["hist"].sum(1), np.full(a["count"], 256 * 256))
