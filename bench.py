@@ -1,18 +1,24 @@
 #!/usr/bin/env python
-"""bench.py — images/sec of the face-crop-plus hot path (detect + align + parse, 1024x1024, bs=256 per GPU).
+"""bench.py — images/sec of the face-crop-plus hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B] [--size S]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c2|c3|c4|c5] [--scaling weak|strong]
 
-One "step" = one pass of detect -> un-pad -> align -> parse over one batch of synthetic uint8 1024x1024 RGB images
-(BASELINE.json configs[2]).  N>1: one process per GPU (torchrun), every rank owns its own batch (weak scaling, images
-are independent), plus ONE all_gather of the per-face landmark/crop metadata per step over NCCL.
+Headline (`--config c3`, the configuration the metric is quoted on): one "step" = one pass of detect -> un-pad -> align
+-> parse over one batch of synthetic uint8 1024x1024 RGB images, bs=256 per GPU.  N>1: one process per GPU (torchrun),
+every rank owns its shard of the batch (weak scaling: 256 per GPU; `--scaling strong`: 256 in total), plus the ONE
+collective of the path: an all-gather of the per-face landmark/crop metadata, issued by the library on a side stream over
+NCCL and overlapped with the parser (`fcp_set_gather`).
 
-`value`  : device-resident inputs and outputs (HBM), CUDA-event timed, max over ranks.
-`e2e`    : same call through the C ABI with HOST pinned buffers — H2D of the batch and D2H of crops/labels/metadata
-           inside the timed region.
-`roofline`: the convolution kernel (dominant: >90% of the step), algorithmic FLOPs / CUDA-event time per launch.
-`cpu_baseline` / `--impl reference`: the oracle (CPU restatement of the reference's torch/cv2 path, pinned to the
-           reference's outputs) on a bounded sample, all host threads.
+`value`    : device-resident inputs and outputs (HBM), CUDA-event timed, max over ranks.
+`e2e`      : the same C-ABI call with HOST pinned buffers — H2D of the batch and D2H of crops/labels/metadata inside the
+             timed region.
+`roofline` : the convolution kernel (dominant: >90% of the step): algorithmic FLOPs / CUDA-event time of its launches.
+`stages_ms`: event pairs around the stages of the path (detector net, decode+NMS, align, parser net, parser tail, gather).
+`secondary`: the other BASELINE.json configurations (c2 detect+align bs=64, c4 RRDBNet x4 bs=32 256->1024, c5 full pipeline
+             with ingest + enhancement on mixed resolutions) and the headline re-run with the 3xTF32 convolution mode.
+`cpu_baseline` / `--impl reference`: the UNMODIFIED reference (pip-installed into baseline/_ref) running the same path
+             (as_batch -> as_tensor -> RetinaFace.predict -> crop_align -> BiSeNet.predict) on the host cores, on a
+             bounded sample; falls back to the oracle port when baseline/_ref is absent.
 """
 from __future__ import annotations
 
@@ -21,8 +27,10 @@ import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
+import types
 from pathlib import Path
 
 import numpy as np
@@ -31,22 +39,26 @@ REPO = Path(__file__).resolve().parent
 sys.path.insert(0, str(REPO))
 
 METRIC = "images/sec (detect+align+parse, 1024x1024, bs=256 per GPU)"
-GFLOP_PER_IMAGE = 253.41          # 226.635 detect + 26.775 parse (1 face / image)
+CONV_IMPLS = ["cuda-core-fp32", "tcgen05-3xTF32", "tcgen05-3xFP16-block-scaled"]
+MIXED_SIZES = [(281, 500), (1080, 1920), (768, 1024), (2464, 1648), (512, 512), (1500, 1000), (480, 640), (1200, 1600)]
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--config", default="c3", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU (0 = the configuration's own)")
     ap.add_argument("--size", type=int, default=1024)
     ap.add_argument("--class-bias", type=float, default=4.8)
     ap.add_argument("--det-mb", type=int, default=16)
     ap.add_argument("--par-mb", type=int, default=32)
     ap.add_argument("--conv-impl", type=int, default=int(os.environ.get("FCP_CONV_IMPL", "2")))
-    ap.add_argument("--cpu-sample", type=int, default=4, help="images in the cpu_baseline sample (0 = skip)")
+    ap.add_argument("--cpu-sample", type=int, default=8, help="images in the cpu_baseline sample (0 = skip)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary configurations")
     return ap.parse_args()
 
 
@@ -57,6 +69,13 @@ def synthetic_batch(batch: int, size: int) -> np.ndarray:
     base = synth.make_images(min(batch, 16), size, size, seed=1234)
     reps = -(-batch // len(base))
     return np.ascontiguousarray(np.concatenate([base] * reps)[:batch])
+
+
+def synthetic_mixed(batch: int) -> list[np.ndarray]:
+    """Ragged uint8 images of MIXED_SIZES (BASELINE.json configs[4]: mixed-resolution input of `as_batch`)."""
+    from face_crop_plus_b200 import synth
+    base = [synth.make_images(1, h, w, seed=4000 + i)[0] for i, (h, w) in enumerate(MIXED_SIZES)]
+    return [base[i % len(base)] for i in range(batch)]
 
 
 class ClockSampler:
@@ -104,177 +123,448 @@ def measured_peaks():
     return 1400.0, 6650.0, "fallback"
 
 
-# ------------------------------------------------------------------------------------------------ CPU baseline
-def cpu_pipeline_images_per_sec(n_images: int, size: int, class_bias: float, repeats: int = 1):
-    """The oracle's process_batch (reference CPU path restated) on `n_images` images; returns (img/s, cores)."""
+def committed_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` summary (profiles/r2_traffic.json)."""
+    p = REPO / "profiles" / "r2_traffic.json"
+    try:
+        return json.loads(p.read_text())
+    except (OSError, ValueError):
+        return None
+
+
+# ------------------------------------------------------------------------------------------------ CPU baselines
+def reference_available() -> bool:
+    return (REPO / "baseline" / "_ref" / "face_crop_plus" / "cropper.py").exists()
+
+
+_REF = {}
+
+
+def load_reference(class_bias: float):
+    """Imports the UNMODIFIED reference from baseline/_ref (pip --target install of /root/reference) with the seeded synthetic
+    checkpoints in its torch.hub cache (trained weights are unobtainable offline).  `unidecode` (used only by the CLI's
+    clean_names) is not in the image: an empty stub module stands in."""
+    if _REF:
+        return _REF
     import torch
     from face_crop_plus_b200 import synth
-    from oracle import pipeline
+    home = tempfile.mkdtemp(prefix="fcp_ref_hub_")
+    os.environ["TORCH_HOME"] = home
+    ckpt = Path(home) / "hub" / "checkpoints"
+    ckpt.mkdir(parents=True, exist_ok=True)
+    for model, fname in synth.REFERENCE_FILENAMES.items():
+        kw = {"class_bias": class_bias} if model == "retinaface" else {}
+        torch.save(synth.make_state_dict(model, 0, **kw), ckpt / fname)
+    sys.modules.setdefault("unidecode", types.ModuleType("unidecode"))
+    sys.path.insert(0, str(REPO / "baseline" / "_ref"))
+    from face_crop_plus import utils as rutils
+    from face_crop_plus.cropper import Cropper
+    _REF.update(Cropper=Cropper, utils=rutils)
+    return _REF
+
+
+def cpu_reference_images_per_sec(n_images: int, size: int, class_bias: float):
+    """The reference's own classes on the host cores: the detect branch of Cropper.process_batch (cropper.py:815-847)
+    without file I/O.  Returns (img/s, cores, faces, seconds)."""
+    import torch
     torch.set_num_threads(os.cpu_count() or 1)
     try:
         import cv2
         cv2.setNumThreads(-1)
     except ImportError:
         pass
+    ref = load_reference(class_bias)
+    ru = ref["utils"]
+    if "cropper" not in _REF:
+        _REF["cropper"] = ref["Cropper"](output_size=256, resize_size=size, strategy="largest", det_threshold=0.6, enh_threshold=None,
+                                         mask_groups={"skin": [1]}, batch_size=n_images, device="cpu")
+    c = _REF["cropper"]
+    imgs = list(synthetic_batch(n_images, size))
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        batch, _, paddings = ru.as_batch(imgs, c.resize_size)
+        x = ru.as_tensor(batch, c.device)
+        landmarks, indices = c.det_model.predict(x)
+        landmarks -= paddings[indices][:, None, [2, 0]]
+        crops = c.crop_align(ru.as_numpy(x), paddings, indices, landmarks)
+        c.par_model.predict(ru.as_tensor(crops, c.device))
+    dt = time.perf_counter() - t0
+    return n_images / dt, torch.get_num_threads(), len(indices), dt
+
+
+def cpu_port_images_per_sec(n_images: int, size: int, class_bias: float):
+    """Fallback when baseline/_ref is absent: the oracle's process_batch (the reference's CPU algorithm restated)."""
+    import torch
+    from face_crop_plus_b200 import synth
+    from oracle import pipeline
+    torch.set_num_threads(os.cpu_count() or 1)
     imgs = synthetic_batch(n_images, size)
     det_sd = synth.make_state_dict("retinaface", 0, class_bias=class_bias)
     par_sd = synth.make_state_dict("bisenet", 0)
-    best = None
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        out = pipeline.process_batch(imgs, det_sd, par_sd, strategy="largest", batch_size=n_images)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return n_images / best, torch.get_num_threads(), len(out["indices"])
+    t0 = time.perf_counter()
+    out = pipeline.process_batch(imgs, det_sd, par_sd, strategy="largest", batch_size=n_images)
+    dt = time.perf_counter() - t0
+    return n_images / dt, torch.get_num_threads(), len(out["indices"]), dt
+
+
+def cpu_baseline(n_images: int, size: int, class_bias: float) -> dict:
+    if reference_available():
+        ips, cores, faces, dt = cpu_reference_images_per_sec(n_images, size, class_bias)
+        kind, what = "reference", ("unmodified face_crop_plus 1.1.0 from baseline/_ref: as_batch -> as_tensor -> RetinaFace.predict -> "
+                                   "crop_align -> BiSeNet.predict")
+    else:
+        ips, cores, faces, dt = cpu_port_images_per_sec(n_images, size, class_bias)
+        kind, what = "port", "oracle.pipeline.process_batch (baseline/_ref not installed)"
+    return {"value": ips, "unit": "images/sec", "cores": cores, "kind": kind,
+            "sample": f"{n_images} images of {size}x{size} in one batch ({faces} faces, {dt:.1f} s), same synthetic workload; {what}"}
 
 
 def run_reference(args, rank: int):
     if rank != 0:
         return
     sample = max(args.cpu_sample, 2)
-    times = []
+    times, last = [], None
     for i in range(args.warmup + args.steps):
-        ips, cores, faces = cpu_pipeline_images_per_sec(sample, args.size, args.class_bias)
+        last = cpu_baseline(sample, args.size, args.class_bias)
         if i >= args.warmup:
-            times.append(sample / ips)
-        if i >= 1 and sum(times) > 120:           # keep the whole arm within a few minutes
+            times.append(sample / last["value"])
+        if i >= 1 and sum(times) > 150:           # keep the whole arm within a few minutes
             break
+    if not times:
+        times.append(sample / last["value"])
     ms = 1e3 * float(np.mean(times))
     value = sample / (ms / 1e3)
+    last["value"] = value
+    last["sample"] = f"{sample} images/step x {len(times)} steps; " + last["sample"]
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": args.gpus,
             "steps": len(times), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"detect+align+parse, {args.size}x{args.size}, strategy=largest; CPU sample of {sample} images per step",
                        "l2": "n/a (CPU)"},
-            "cpu_baseline": {"value": value, "unit": "images/sec", "cores": cores, "kind": "port",
-                             "sample": f"{sample} images/step x {len(times)} steps, oracle.pipeline.process_batch (torch CPU + numpy), {faces} faces"},
+            "cpu_baseline": last,
             "e2e": {"value": value, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 # --------------------------------------------------------------------------------------------------- GPU arm
-def run_b200(args, rank: int, world: int, local_rank: int):
-    import torch
-    import torch.distributed as dist
-    from face_crop_plus_b200 import _abi, synth
-    from face_crop_plus_b200.landmarks import landmarks_target
+class Harness:
+    """Shared timing plumbing of the GPU arm: barrier + sync on both sides, CUDA events on the library's stream, max over ranks."""
 
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    ctx = _abi.Context(local_rank)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-    ctx.set_micro_batch(args.det_mb, args.par_mb)
-    ctx.set_conv_impl(args.conv_impl)
-    ctx.load_state_dict(_abi.MODEL_RETINAFACE, synth.make_state_dict("retinaface", 0, class_bias=args.class_bias))
-    ctx.load_state_dict(_abi.MODEL_BISENET, synth.make_state_dict("bisenet", 0))
-
-    B, S = args.batch, args.size
-    host_images = torch.from_numpy(synthetic_batch(B, S)).pin_memory()
-    dev_images = host_images.to(dev)
-    target = landmarks_target((256, 256), 0.65)
-    cap = B
-
-    def outputs(device):
-        kw = dict(device=device) if device is not None else dict(pin_memory=True)
-        return dict(landmarks=torch.zeros((cap, 5, 2), dtype=torch.float32, **kw), indices=torch.zeros(cap, dtype=torch.int32, **kw),
-                    crops=torch.zeros((cap, 256, 256, 3), dtype=torch.uint8, **kw),
-                    matrices=torch.zeros((cap, 2, 3), dtype=torch.float64, **kw), valid=torch.zeros(cap, dtype=torch.uint8, **kw),
-                    labels=torch.zeros((cap, 256, 256), dtype=torch.uint8, **kw), hist=torch.zeros((cap, 19), dtype=torch.int32, **kw))
-
-    dev_out, host_out = outputs(dev), outputs(None)
-    from face_crop_plus_b200 import distributed as D
-    faces_seen = []
-
-    def step(images, out):
-        res = ctx.pipeline(images, None, target, (256, 256), 0.6, 0.4, "largest", "constant", False, True, cap, out, B, S, S)
-        faces_seen.append(res["count"])
+    def __init__(self, args, rank, world, local_rank):
+        import torch
+        import torch.distributed as dist
+        from face_crop_plus_b200 import _abi, synth
+        self.torch, self.dist, self.abi, self.synth = torch, dist, _abi, synth
+        self.args, self.rank, self.world = args, rank, world
+        torch.cuda.set_device(local_rank)
+        self.dev = torch.device("cuda", local_rank)
         if world > 1:
-            # the one collective of the path: landmark / index / matrix metadata of every rank's faces (SURVEY.md §8e)
-            k = res["count"]
-            rec = D.pack_records(out["landmarks"][:k].cpu().numpy(), out["indices"][:k].cpu().numpy(),
-                                 out["matrices"][:k].cpu().numpy(), out["valid"][:k].cpu().numpy(), rank * B)
-            D.gather_records(rec, cap, device=dev)
-        return res
-
-    def barrier():
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.ctx = _abi.Context(local_rank)
+        self.ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        self.ctx.set_micro_batch(args.det_mb, args.par_mb)
+        self.ctx.set_conv_impl(args.conv_impl)
+        self.loaded = set()
         if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+            from face_crop_plus_b200 import distributed as D
+            D.init_comm(self.ctx)
 
-    def timed(images, out, steps):
-        barrier()
+    def need(self, *models):
+        for m in models:
+            if m in self.loaded:
+                continue
+            kw = {"class_bias": self.args.class_bias} if m == "retinaface" else {}
+            mid = {"retinaface": self.abi.MODEL_RETINAFACE, "bisenet": self.abi.MODEL_BISENET, "rrdbnet": self.abi.MODEL_RRDBNET}[m]
+            self.ctx.load_state_dict(mid, self.synth.make_state_dict(m, 0, **kw))
+            self.loaded.add(m)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, fn, steps):
+        """(max-over-ranks total ms, [per-rank total ms])"""
+        torch = self.torch
+        self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
-            step(images, out)
+            fn()
         e1.record()
-        barrier()
+        self.barrier()
         ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        per_rank = [ms]
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.dev)
+            allt = [torch.zeros_like(t) for _ in range(self.world)]
+            self.dist.all_gather(allt, t)
+            per_rank = [float(x.item()) for x in allt]
+        return max(per_rank), per_rank
 
-    for _ in range(args.warmup):
+
+def pipeline_outputs(torch, cap, device, parse=True):
+    kw = dict(device=device) if device is not None else dict(pin_memory=True)
+    out = dict(landmarks=torch.zeros((cap, 5, 2), dtype=torch.float32, **kw), indices=torch.zeros(cap, dtype=torch.int32, **kw),
+               crops=torch.zeros((cap, 256, 256, 3), dtype=torch.uint8, **kw),
+               matrices=torch.zeros((cap, 2, 3), dtype=torch.float64, **kw), valid=torch.zeros(cap, dtype=torch.uint8, **kw))
+    if parse:
+        out.update(labels=torch.zeros((cap, 256, 256), dtype=torch.uint8, **kw), hist=torch.zeros((cap, 19), dtype=torch.int32, **kw))
+    return out
+
+
+def bench_pipeline(hx: Harness, B: int, S: int, parse: bool, steps: int, warmup: int, e2e_steps: int, profile: bool):
+    """detect -> un-pad -> align (-> parse) over B images of SxS per rank.  Returns a dict of measurements."""
+    torch, ctx = hx.torch, hx.ctx
+    from face_crop_plus_b200.landmarks import landmarks_target
+    hx.need("retinaface", *(["bisenet"] if parse else []))
+    host_images = torch.from_numpy(synthetic_batch(B, S)).pin_memory()
+    dev_images = host_images.to(hx.dev)
+    target = landmarks_target((256, 256), 0.65)
+    cap = B
+    dev_out, host_out = pipeline_outputs(torch, cap, hx.dev, parse), pipeline_outputs(torch, cap, None, parse)
+    gathered = None
+    if hx.world > 1:
+        # the one collective of the path: every rank's face records, all-gathered on the device by the library
+        gathered = torch.zeros((hx.world, cap + 1, 20), dtype=torch.float64, device=hx.dev)
+        ctx.set_gather(gathered, cap, hx.rank * B)
+    faces_seen = []
+
+    def step(images, out):
+        res = ctx.pipeline(images, None, target, (256, 256), 0.6, 0.4, "largest", "constant", False, parse, cap, out, B, S, S)
+        faces_seen.append(res["count"])
+
+    for _ in range(warmup):
         step(dev_images, dev_out)
+    if profile:
+        ctx.profile(True)
+        ctx.profile_read()
+        ctx.profile_stages()
+    l0 = ctx.launch_count()
+    ms_total, per_rank = hx.timed(lambda: step(dev_images, dev_out), steps)
+    launches = ctx.launch_count() - l0
+    prof = stages = None
+    if profile:
+        prof, stages = ctx.profile_read(), ctx.profile_stages()
+        ctx.profile(False)
+    step(host_images, host_out)
+    ms_e2e, _ = hx.timed(lambda: step(host_images, host_out), e2e_steps)
+    faces = faces_seen[-1]
+    total_faces = None
+    if gathered is not None:
+        total_faces = int(gathered[:, cap, 0].sum().item())
+        ctx.set_gather(None)
+    d2h = sum(int(np.prod(host_out[k].shape[1:])) * host_out[k].element_size() for k in host_out) * faces
+    return dict(ms_step=ms_total / steps, per_rank_ms=[t / steps for t in per_rank], launches=launches, prof=prof, stages=stages,
+                ms_e2e_step=ms_e2e / e2e_steps, faces=faces, total_faces=total_faces, h2d=B * S * S * 3, d2h=d2h)
+
+
+def bench_enhance(hx: Harness, B: int, S: int, steps: int, warmup: int):
+    """BASELINE.json configs[3]: RRDBNet x4 + bicubic 1/4 + clamp/round on B uint8 images of SxS (every image enhanced)."""
+    torch, ctx = hx.torch, hx.ctx
+    hx.need("rrdbnet")
+    host = torch.from_numpy(synthetic_batch(B, S)).pin_memory()
+    dev = host.to(hx.dev)
+    work_dev, work_host = dev.clone(), host.clone().pin_memory()
+
+    def step_dev():
+        work_dev.copy_(dev)
+        ctx.enhance_u8(work_dev, None)
+
+    def step_host():
+        work_host.copy_(host)
+        ctx.enhance_u8(work_host, None)
+
+    for _ in range(warmup):
+        step_dev()
     ctx.profile(True)
     ctx.profile_read()
-    l0 = ctx.launch_count()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    ms_total = timed(dev_images, dev_out, args.steps)
-    launches = ctx.launch_count() - l0
+    ms, _ = hx.timed(step_dev, steps)
     prof = ctx.profile_read()
+    ctx.profile_stages()
     ctx.profile(False)
-    # end to end: host pinned inputs and outputs through the same C-ABI call
-    step(host_images, host_out)
-    e2e_steps = max(1, min(args.steps, 3))
-    ms_e2e = timed(host_images, host_out, e2e_steps)
-    clocks = sampler.stop() if sampler else None
-    faces = faces_seen[-1]
+    step_host()
+    e2e_steps = max(1, min(steps, 2))
+    ms_e2e, _ = hx.timed(step_host, e2e_steps)
+    return dict(ms_step=ms / steps, ms_e2e_step=ms_e2e / e2e_steps, prof=prof, bytes=B * S * S * 3)
 
-    cpu = None
-    if rank == 0 and world == 1 and args.cpu_sample > 0:
-        ips, cores, cfaces = cpu_pipeline_images_per_sec(args.cpu_sample, S, args.class_bias)
-        cpu = {"value": ips, "unit": "images/sec", "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_sample} images of {S}x{S} (same synthetic workload, {cfaces} faces), oracle.pipeline.process_batch"}
+
+def bench_full(hx: Harness, B: int, S: int, steps: int, warmup: int):
+    """BASELINE.json configs[4]: ingest (as_batch of mixed-resolution images) -> detect -> enhance (gated) -> align -> parse ->
+    group, per rank.  The enhancement threshold is set from a first detection pass so that ~1 image in 16 is gated on."""
+    torch, ctx = hx.torch, hx.ctx
+    from face_crop_plus_b200.landmarks import landmarks_target
+    hx.need("retinaface", "bisenet", "rrdbnet")
+    images = synthetic_mixed(B)
+    target = landmarks_target((256, 256), 0.65)
+    batch = torch.empty((B, S, S, 3), dtype=torch.uint8, device=hx.dev)
+    attr_groups = {"glasses": [6], "no_accessories": [-6, -9, -15, -18]}
+    mask_groups = {"eyes_and_eyebrows": [2, 3, 4, 5], "skin": [1]}
+    _, _, pads = ctx.as_batch(images, S, out=batch)
+    det = ctx.detect(batch, 0.6, 0.4, "largest", n=B, h=S, w=S)
+    lm = det["landmarks"]
+    factors = np.sort(((lm[:, 4, 0] - lm[:, 0, 0]) * (lm[:, 4, 1] - lm[:, 0, 1]) / np.float32(S * S)).astype(np.float32))
+    k = max(1, len(factors) // 16)
+    thr = float(factors[k - 1]) if len(factors) else 0.0
+    seen = []
+
+    def step():
+        _, _, pads = ctx.as_batch(images, S, out=batch)
+        ctx.set_enhance(thr)
+        try:
+            out = ctx.pipeline(batch, pads, target, (256, 256), 0.6, 0.4, "largest", "constant", False, True, B, None, B, S, S)
+        finally:
+            ctx.set_enhance(None)
+        ctx.group(out["labels"], out["hist"], attr_groups, mask_groups)
+        seen.append(out["count"])
+
+    for _ in range(warmup):
+        step()
+    ctx.profile(True)
+    ctx.profile_read()
+    ctx.profile_stages()
+    ms, _ = hx.timed(step, steps)
+    ctx.profile_read()
+    stages = ctx.profile_stages()
+    ctx.profile(False)
+    n_gated = int((factors <= np.float32(thr)).sum()) if len(factors) else 0
+    return dict(ms_step=ms / steps, stages={k: v / steps for k, v in stages.items()}, threshold=thr, enhanced_per_step=n_gated,
+                faces=seen[-1], h2d=sum(im.nbytes for im in images))
+
+
+def run_b200(args, rank: int, world: int, local_rank: int):
+    hx = Harness(args, rank, world, local_rank)
+    S = args.size
+    per_gpu = {"c2": 64, "c3": 256, "c4": 32, "c5": 64}[args.config]
+    B = args.batch or per_gpu
+    det_mb, par_mb = args.det_mb, args.par_mb
+    if args.scaling == "strong" and world > 1:
+        B = max(1, B // world)
+        det_mb, par_mb = min(det_mb, max(1, B // 2)), min(par_mb, B)     # >= 2 detector micro-batches keep the H2D overlap
+        hx.ctx.set_micro_batch(det_mb, par_mb)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    tensor_peak, hbm_peak, which = measured_peaks()
+    line = None
+    if args.config in ("c2", "c3"):
+        parse = args.config == "c3"
+        e2e_steps = max(2, min(args.steps, 5))
+        r = bench_pipeline(hx, B, S, parse, args.steps, args.warmup, e2e_steps, profile=True)
+        clocks = sampler.stop() if sampler else None
+        if rank == 0:
+            prof, ms_step = r["prof"], r["ms_step"]
+            conv_tflops = prof["conv_flops"] / (prof["conv_ms"] / 1e3) / 1e12 if prof["conv_ms"] else 0.0
+            split = {0: None, 1: 6.0, 2: 3.0}[args.conv_impl]   # MMAs per fp32-equivalent product x (bf16 rate / pipe rate)
+            traffic = committed_traffic() or {}
+            workload = ("detect+align+parse" if parse else "detect+align") + f", {S}x{S} uint8 RGB, bs={B} per GPU, strategy=largest, 256x256 crops"
+            line = {"metric": METRIC if parse else "images/sec (detect+align, 1024x1024, bs=64)", "value": world * B / (ms_step / 1e3),
+                    "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+                    "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "config": {"workload": workload, "global_batch": world * B, "faces_per_step_per_gpu": r["faces"],
+                               "class_bias": args.class_bias, "conv_impl": CONV_IMPLS[args.conv_impl],
+                               "precision": "fp32-equivalent split arithmetic: every product a*w is formed from 11-bit hi/lo parts "
+                                            "(a_hi*w_hi + a_lo*w_hi + a_hi*w_lo) and accumulated in fp32; error vs fp64 <= an fp32 FMA "
+                                            "chain's (tests/test_gpu_parity.py::test_conv2d_tensor_core_accuracy_large_k, "
+                                            "::test_conv2d_f16x3_dynamic_range)",
+                               "micro_batch": [det_mb, par_mb], "parallelism": f"batch-shard x{world}",
+                               "l2": f"inputs larger than L2 ({B * S * S * 3 / 2**20:.0f} MiB batch; activations stream through a "
+                                     f"micro-batched arena)"},
+                    "e2e": {"value": world * B / (r["ms_e2e_step"] / 1e3), "unit": "images/sec", "h2d_bytes_per_step": r["h2d"],
+                            "d2h_bytes_per_step": r["d2h"], "steps": e2e_steps},
+                    "gpu_launches": int(r["launches"]),
+                    "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (all convolution launches of the step)",
+                                 "achieved": conv_tflops, "peak": tensor_peak, "unit": "TFLOP/s", "frac": conv_tflops / tensor_peak,
+                                 "peak_source": f"{which} bf16 sustained (MEASURED_PEAKS.json); achieved = algorithmic fp32-equivalent FLOPs",
+                                 "traffic": traffic.get("dram_bytes_per_launch"), "traffic_source": traffic.get("source"),
+                                 "frac_of_split_ceiling": (conv_tflops / (tensor_peak / split)) if split else None,
+                                 "split_ceiling_tflops": (tensor_peak / split) if split else None,
+                                 "conv_launches_per_step": prof["conv_launches"] // args.steps,
+                                 "conv_ms_per_step": prof["conv_ms"] / args.steps,
+                                 "conv_share_of_step": prof["conv_ms"] / (ms_step * args.steps),
+                                 "algorithmic_gflop_per_image": prof["conv_flops"] / args.steps / B / 1e9,
+                                 "algorithmic_gbytes_per_step": prof["conv_bytes"] / args.steps / 1e9},
+                    "stages_ms": {k: v / args.steps for k, v in r["stages"].items()},
+                    "clocks": clocks}
+            if world > 1:
+                pr = sorted(r["per_rank_ms"])
+                line["ranks_ms_per_step"] = {"min": pr[0], "median": pr[len(pr) // 2], "max": pr[-1]}
+                line["gather"] = {"ms_per_step": r["stages"]["gather"] / args.steps, "faces_gathered": r["total_faces"],
+                                  "how": "device-side pack + ncclAllGather on a side stream, overlapped with the parser (fcp_set_gather)"}
+    elif args.config == "c4":
+        r = bench_enhance(hx, B, 256, args.steps, args.warmup)
+        clocks = sampler.stop() if sampler else None
+        if rank == 0:
+            prof = r["prof"]
+            conv_tflops = prof["conv_flops"] / (prof["conv_ms"] / 1e3) / 1e12 if prof["conv_ms"] else 0.0
+            line = {"metric": "images/sec (RRDBNet x4 enhancement, 256x256 -> 1024x1024, bs=32)", "value": world * B / (r["ms_step"] / 1e3),
+                    "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_step"],
+                    "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "config": {"workload": f"RRDBNet.predict on {B} uint8 256x256 images per GPU, every image enhanced",
+                               "conv_impl": CONV_IMPLS[args.conv_impl]},
+                    "e2e": {"value": world * B / (r["ms_e2e_step"] / 1e3), "unit": "images/sec", "h2d_bytes_per_step": r["bytes"],
+                            "d2h_bytes_per_step": r["bytes"]},
+                    "roofline": {"bound": "tensor", "achieved": conv_tflops, "peak": tensor_peak, "unit": "TFLOP/s",
+                                 "frac": conv_tflops / tensor_peak, "traffic": None},
+                    "clocks": clocks}
+    else:
+        steps5, warm5 = max(1, min(args.steps, 3)), min(args.warmup, 1)
+        r = bench_full(hx, B, S, steps5, warm5)
+        clocks = sampler.stop() if sampler else None
+        if rank == 0:
+            line = {"metric": "images/sec (ingest+detect+enhance+align+parse+group, mixed resolution)", "value": world * B / (r["ms_step"] / 1e3),
+                    "unit": "images/sec", "n_gpus": world, "steps": steps5, "warmup": warm5, "ms_per_step": r["ms_step"],
+                    "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "config": {"workload": f"{B} images per GPU of {MIXED_SIZES} (h, w) -> as_batch {S}x{S} -> detect -> enhance (gate <= "
+                                           f"{r['threshold']:.3g}: {r['enhanced_per_step']} images/step) -> align -> parse -> group",
+                               "conv_impl": CONV_IMPLS[args.conv_impl]},
+                    "e2e": {"value": world * B / (r["ms_step"] / 1e3), "unit": "images/sec", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": None,
+                            "note": "the step already starts from host images (as_batch copies them H2D) and returns host crops/labels"},
+                    "stages_ms": r["stages"], "clocks": clocks}
+
+    # ---- secondary configurations: the other BASELINE.json configs + the 3xTF32 convolution mode (N=1), strong scaling (N>1)
+    if args.config == "c3" and not args.no_secondary and args.scaling == "weak":
+        sec = {}
+        try:
+            if world == 1:
+                r2 = bench_pipeline(hx, 64, S, False, 3, 1, 2, profile=False)
+                sec["c2_detect_align_bs64"] = {"value": 64 / (r2["ms_step"] / 1e3), "unit": "images/sec", "ms_per_step": r2["ms_step"],
+                                               "e2e": 64 / (r2["ms_e2e_step"] / 1e3)}
+                r4 = bench_enhance(hx, 32, 256, 2, 1)
+                p4 = r4["prof"]
+                sec["c4_rrdbnet_x4_bs32_256"] = {"value": 32 / (r4["ms_step"] / 1e3), "unit": "images/sec", "ms_per_step": r4["ms_step"],
+                                                 "e2e": 32 / (r4["ms_e2e_step"] / 1e3),
+                                                 "conv_tflops": p4["conv_flops"] / (p4["conv_ms"] / 1e3) / 1e12 if p4["conv_ms"] else None}
+                r5 = bench_full(hx, 64, S, 2, 1)
+                sec["c5_full_mixed_res_bs64"] = {"value": 64 / (r5["ms_step"] / 1e3), "unit": "images/sec", "ms_per_step": r5["ms_step"],
+                                                 "enhanced_images_per_step": r5["enhanced_per_step"], "stages_ms": r5["stages"]}
+                hx.ctx.set_conv_impl(1)
+                r1 = bench_pipeline(hx, B, S, True, 3, 1, 2, profile=True)
+                p1 = r1["prof"]
+                sec["c3_conv_3xTF32"] = {"value": B / (r1["ms_step"] / 1e3), "unit": "images/sec", "ms_per_step": r1["ms_step"],
+                                         "e2e": B / (r1["ms_e2e_step"] / 1e3),
+                                         "conv_tflops": p1["conv_flops"] / (p1["conv_ms"] / 1e3) / 1e12 if p1["conv_ms"] else None}
+                hx.ctx.set_conv_impl(args.conv_impl)
+            else:
+                # the metric's own global batch (256 images in total): strong scaling of the same path
+                Bs = max(1, 256 // world)
+                hx.ctx.set_micro_batch(min(det_mb, max(1, Bs // 2)), min(par_mb, Bs))
+                rs = bench_pipeline(hx, Bs, S, True, 3, 2, 2, profile=False)
+                sec["c3_strong_global_bs256"] = {"value": world * Bs / (rs["ms_step"] / 1e3), "unit": "images/sec", "ms_per_step": rs["ms_step"],
+                                                 "images_per_gpu": Bs, "e2e": world * Bs / (rs["ms_e2e_step"] / 1e3)}
+                hx.ctx.set_micro_batch(det_mb, par_mb)
+        except Exception as e:          # a secondary number must never take the headline down with it
+            sec["error"] = repr(e)
+        if rank == 0 and line is not None:
+            line["secondary"] = sec
+    if rank == 0 and world == 1 and args.cpu_sample > 0 and args.config == "c3":
+        try:
+            line["cpu_baseline"] = cpu_baseline(args.cpu_sample, S, args.class_bias)
+        except Exception as e:
+            line["cpu_baseline"] = {"error": repr(e)}
     if rank == 0:
-        tensor_peak, hbm_peak, which = measured_peaks()
-        ms_step = ms_total / args.steps
-        value = world * B / (ms_step / 1e3)
-        conv_tflops = prof["conv_flops"] / (prof["conv_ms"] / 1e3) / 1e12 if prof["conv_ms"] else 0.0
-        h2d = B * S * S * 3
-        d2h = sum(int(np.prod(host_out[k].shape[1:])) * host_out[k].element_size() for k in host_out) * faces
-        line = {"metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic",
-                "config": {"workload": f"detect+align+parse, {S}x{S} uint8 RGB, bs={B} per GPU, strategy=largest, 256x256 crops",
-                           "global_batch": world * B, "faces_per_step_per_gpu": faces, "class_bias": args.class_bias,
-                           "conv_impl": ["cuda-core-fp32", "tcgen05-3xTF32", "tcgen05-3xFP16-block-scaled"][args.conv_impl],
-                           "micro_batch": [args.det_mb, args.par_mb], "parallelism": f"batch-shard x{world}",
-                           "l2": f"inputs larger than L2 ({B * S * S * 3 / 2**20:.0f} MiB batch; activations stream through a "
-                                 f"micro-batched arena)"},
-                "e2e": {"value": world * B / (ms_e2e / e2e_steps / 1e3), "unit": "images/sec", "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": d2h, "steps": e2e_steps},
-                "gpu_launches": int(launches),
-                "roofline": {"bound": "tensor", "kernel": "conv (all launches of the step)", "achieved": conv_tflops,
-                             "peak": tensor_peak, "unit": "TFLOP/s", "frac": conv_tflops / tensor_peak,
-                             "peak_source": f"{which} bf16 sustained; the kernel is exact-fp32 (parity bar), see DESIGN.md",
-                             "traffic": None,
-                             # an fp32-equivalent result costs 3 TF32 MMAs at half the bf16 rate: ceiling = peak / 6
-                             "frac_of_3xtf32_ceiling": conv_tflops / (tensor_peak / 6.0),
-                             "conv_launches_per_step": prof["conv_launches"] // args.steps,
-                             "conv_ms_per_step": prof["conv_ms"] / args.steps,
-                             "conv_share_of_step": prof["conv_ms"] / ms_total,
-                             "algorithmic_gflop_per_image": prof["conv_flops"] / args.steps / B / 1e9},
-                "clocks": clocks}
-        if cpu:
-            line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        hx.dist.barrier()
+        hx.dist.destroy_process_group()
 
 
 def main():

@@ -37,6 +37,7 @@ SIGNATURES = {
     "fcp_set_conv_impl": (_i, [_p, _i]),
     "fcp_profile": (_i, [_p, _i]),
     "fcp_profile_read": (_i, [_p, C.POINTER(C.c_double)]),
+    "fcp_profile_stages": (_i, [_p, C.POINTER(C.c_double)]),
     "fcp_load_tensor": (_i, [_p, _i, C.c_char_p, _p, C.POINTER(C.c_int64), _i]),
     "fcp_finalize": (_i, [_p, _i, _i]),
     "fcp_detect": (_i, [_p, _p, _i, _i, _i, _f, _f, _i, _i, _p, _p, _p, _p, _p, _p]),
@@ -53,6 +54,14 @@ SIGNATURES = {
     "fcp_group": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _i, _i, _i, _p, _i, _i, _p, _p, _p]),
     "fcp_enhance": (_i, [_p, _p, _i, _i, _i, _p]),
     "fcp_enhance_forward": (_i, [_p, _p, _i, _i, _i, _p]),
+    "fcp_enhance_u8": (_i, [_p, _p, _i, _i, _i, _p]),
+    "fcp_enhance_gate": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _p]),
+    "fcp_set_enhance": (_i, [_p, _f]),
+    "fcp_comm_unique_id": (_i, [_p, _p]),
+    "fcp_comm_init": (_i, [_p, _i, _i, _p]),
+    "fcp_comm_destroy": (None, [_p]),
+    "fcp_allgather_meta": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "fcp_set_gather": (_i, [_p, _p, _i, _i]),
     "fcp_pipeline": (_i, [_p, _p, _i, _i, _i, _p, _f, _f, _i, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
     "fcp_conv2d": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _p, _p, _p, _i, _f, _i, _p]),
 }
@@ -148,6 +157,41 @@ class Context:
         out = (C.c_double * 4)()
         self.check(self.lib.fcp_profile_read(self.h, out))
         return dict(conv_ms=out[0], conv_launches=int(out[1]), conv_flops=out[2], conv_bytes=out[3])
+
+    STAGES = ("detect_net", "detect_post", "enhance", "align", "parse_net", "parse_tail", "gather", "ingest")
+
+    def profile_stages(self) -> dict:
+        """Milliseconds per stage accumulated since the last read (only while ``profile(True)``)."""
+        out = (C.c_double * 8)()
+        self.check(self.lib.fcp_profile_stages(self.h, out))
+        return dict(zip(self.STAGES, [float(v) for v in out]))
+
+    # ---- multi-GPU: the one collective (metadata all-gather over NCCL)
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        self.check(self.lib.fcp_comm_unique_id(self.h, buf))
+        return buf.raw
+
+    def comm_init(self, rank: int, world: int, unique_id: bytes | None):
+        self.check(self.lib.fcp_comm_init(self.h, int(rank), int(world), unique_id))
+        self.comm_rank, self.comm_world = int(rank), int(world)
+
+    def set_gather(self, out_records, cap: int = 0, index_base: int = 0):
+        """``out_records``: CUDA float64 tensor [world, cap + 1, 20] (or None = off); see ``fcp_set_gather``."""
+        self.check(self.lib.fcp_set_gather(self.h, _ptr(out_records), int(cap), int(index_base)))
+        self._gather_keepalive = out_records
+
+    def allgather_meta(self, landmarks, indices, matrices, valid, cap: int, index_base: int, out_records=None):
+        """Explicit form of the collective: returns float64 [world, cap + 1, 20] (numpy unless ``out_records`` is given)."""
+        f = len(indices)
+        world = getattr(self, "comm_world", 1)
+        lms = np.ascontiguousarray(landmarks, dtype=np.float32).reshape(f, 10) if not hasattr(landmarks, "data_ptr") else landmarks
+        idx = np.ascontiguousarray(indices, dtype=np.int32) if not hasattr(indices, "data_ptr") else indices
+        mats = None if matrices is None else (np.ascontiguousarray(matrices, dtype=np.float64) if not hasattr(matrices, "data_ptr") else matrices)
+        val = None if valid is None else (np.ascontiguousarray(valid, dtype=np.uint8) if not hasattr(valid, "data_ptr") else valid)
+        out = np.zeros((world, cap + 1, 20), np.float64) if out_records is None else out_records
+        self.check(self.lib.fcp_allgather_meta(self.h, _ptr(lms), _ptr(idx), _ptr(mats), _ptr(val), f, int(cap), int(index_base), _ptr(out)))
+        return out
 
     def load_state_dict(self, model: int, state_dict, rrdb_blocks: int = 23):
         """Feeds a reference-format state_dict (torch tensors or numpy arrays) and finalizes the model."""
@@ -318,6 +362,25 @@ class Context:
         g = None if gate is None else np.ascontiguousarray(gate, dtype=np.uint8)
         self.check(self.lib.fcp_enhance(self.h, _ptr(images_nchw), n, h, w, _ptr(g)))
         return images_nchw
+
+    def enhance_u8(self, images_nhwc, gate=None):
+        """In place on a uint8 [n,h,w,3] numpy array or CUDA tensor (``fcp_enhance_u8``)."""
+        n, h, w = images_nhwc.shape[:3]
+        g = None if gate is None else np.ascontiguousarray(gate, dtype=np.uint8)
+        self.check(self.lib.fcp_enhance_u8(self.h, _ptr(images_nhwc), n, h, w, _ptr(g)))
+        return images_nhwc
+
+    def enhance_gate(self, landmarks, indices, n: int, h: int, w: int, min_face_factor: float) -> np.ndarray:
+        """Device evaluation of the gate of ``RRDBNet.predict`` (rrdb.py:124-141): uint8 [n]."""
+        idx = np.ascontiguousarray(indices, dtype=np.int32)
+        lms = np.ascontiguousarray(landmarks, dtype=np.float32).reshape(len(idx), 10)
+        out = np.zeros(n, np.uint8)
+        self.check(self.lib.fcp_enhance_gate(self.h, _ptr(lms), _ptr(idx), len(idx), n, h, w, float(min_face_factor), _ptr(out)))
+        return out
+
+    def set_enhance(self, min_face_factor: float | None):
+        """Enhancement stage of :meth:`pipeline`: the ``min_face_factor`` of ``RRDBNet`` or None = off."""
+        self.check(self.lib.fcp_set_enhance(self.h, -1.0 if min_face_factor is None else float(min_face_factor)))
 
     def enhance_forward(self, x_nchw):
         x = np.ascontiguousarray(x_nchw, dtype=np.float32)

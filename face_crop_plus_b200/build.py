@@ -10,7 +10,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libfcpb200.so"
-SOURCES = ["runtime.cu", "graphs.cu", "conv_ffma.cu", "conv_tc.cu", "misc.cu", "det_post.cu", "align.cu", "parse.cu", "ingest.cu"]
+SOURCES = ["runtime.cu", "graphs.cu", "conv_ffma.cu", "conv_tc.cu", "misc.cu", "det_post.cu", "align.cu", "parse.cu", "ingest.cu", "comm.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xcompiler", "-Wall", "-Xcompiler", "-ffp-contract=off", "-Xcudafe", "--diag_suppress=177",
@@ -44,7 +44,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         list(pool.map(run, jobs))
     objs = [str(objdir / (n + ".o")) for n in SOURCES]
     if jobs or not LIB.exists():
-        run([NVCC, "-shared", "-o", str(LIB), *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"])
+        run([NVCC, "-shared", "-o", str(LIB), *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-ldl"])
     return LIB
 
 

@@ -18,7 +18,7 @@ import torch
 
 from . import _abi
 from .landmarks import landmarks_target
-from .models import BiSeNet, RetinaFace, RRDBNet, _lock, get_context
+from .models import BiSeNet, RetinaFace, RRDBNet, _lock, bind_stream, get_context
 from .utils import as_batch, get_ldm_slices, parse_landmarks_file, read_images
 
 
@@ -69,6 +69,7 @@ class Cropper:
             return np.array([])
         imgs = list(images) if isinstance(images, (list, tuple)) else np.ascontiguousarray(images)
         with _lock:
+            bind_stream(self.ctx)
             crops, _, valid = self.ctx.align(imgs, padding, indices, landmarks_source, self.landmarks_target,
                                              self.output_size, self.padding, self.allow_skew)
         return crops[valid] if valid.any() else np.array([])       # un-estimable transforms are skipped (:529-531)
@@ -123,17 +124,14 @@ class Cropper:
                 ldm_rows += rows.tolist()
             landmarks = self.landmarks[0][ldm_rows]
         else:
-            if self.enh_model is None:
-                # ingest straight into a device batch: resize + pad (fcp_as_batch) and the detect -> align -> parse call
-                # share it, the images never come back to the host between the two
-                batch = torch.empty((len(images), self.resize_size[1], self.resize_size[0], 3), dtype=torch.uint8,
-                                    device=self.device)
-                with _lock:
-                    _, _, paddings = self.ctx.as_batch(images, self.resize_size, out=batch)
-                return self._process_detected_batch(batch, paddings, file_names, output_dir)
-            images, _, paddings = as_batch(images, self.resize_size, ctx=self.ctx)
-            landmarks, indices = self.det_model.predict_u8(images)
-            landmarks = landmarks - paddings[indices][:, None, [2, 0]] if len(indices) else landmarks   # :822
+            # ingest straight into a device batch: resize + pad (fcp_as_batch) and the detect -> (enhance) -> align -> parse
+            # call share it, the images never come back to the host between the stages
+            batch = torch.empty((len(images), self.resize_size[1], self.resize_size[0], 3), dtype=torch.uint8,
+                                device=self.device)
+            with _lock:
+                bind_stream(self.ctx)
+                _, _, paddings = self.ctx.as_batch(images, self.resize_size, out=batch)
+            return self._process_detected_batch(batch, paddings, file_names, output_dir)
         if landmarks is not None and len(landmarks) == 0:
             return
         if landmarks is not None and landmarks.shape[1] != self.num_std_landmarks:
@@ -141,14 +139,8 @@ class Cropper:
             with _lock:
                 landmarks = self.ctx.reduce_landmarks(landmarks)               # the slice means, on the device
         if self.enh_model is not None:
-            if isinstance(images, np.ndarray):
-                x = torch.from_numpy(images).to(self.enh_model.device).permute(0, 3, 1, 2).float().contiguous()
-                x = self.enh_model.predict(x, landmarks, indices)
-                images = x.permute(0, 2, 3, 1).to(torch.uint8).contiguous().cpu().numpy()          # as_numpy, utils.py:194
-            else:
-                xs = [torch.from_numpy(im).to(self.enh_model.device).permute(2, 0, 1).float().contiguous() for im in images]
-                xs = self.enh_model.predict(xs, landmarks, indices)
-                images = [x.permute(1, 2, 0).to(torch.uint8).contiguous().cpu().numpy() for x in xs]
+            # no detector: the images are the caller's ragged list (cropper.py:833-836 on a list of tensors); uint8 in/out
+            images = self.enh_model.predict_u8(list(images), landmarks, indices)
         if landmarks is not None:
             images = self.crop_align(images, paddings, indices, landmarks)
         if self.par_model is not None and len(images):
@@ -156,14 +148,20 @@ class Cropper:
         self.save_groups(images, file_names[indices], output_dir, *groups)
 
     def _process_detected_batch(self, images, paddings, file_names, output_dir):
-        """detect -> un-pad -> align -> parse of cropper.py:815-847 as ONE library call on the uint8 batch."""
+        """detect -> un-pad -> (enhance) -> align -> parse of cropper.py:815-847 as ONE library call on the uint8 batch."""
         with _lock:
+            bind_stream(self.ctx)
             if self.par_model is not None:
                 self.ctx.set_micro_batch(16, max(int(self.batch_size), 1))
             batch = images if hasattr(images, "data_ptr") else np.ascontiguousarray(images)
-            out = self.ctx.pipeline(batch, paddings, self.landmarks_target, self.output_size,
-                                    self.det_threshold, self.det_model.nms_threshold, self.strategy, self.padding,
-                                    self.allow_skew, parse=self.par_model is not None)
+            # enhancement (cropper.py:833-836) is a stage of the same call: gate, RRDBNet and the warp source stay on the device
+            self.ctx.set_enhance(self.enh_model.min_face_factor if self.enh_model is not None else None)
+            try:
+                out = self.ctx.pipeline(batch, paddings, self.landmarks_target, self.output_size,
+                                        self.det_threshold, self.det_model.nms_threshold, self.strategy, self.padding,
+                                        self.allow_skew, parse=self.par_model is not None)
+            finally:
+                self.ctx.set_enhance(None)
         if out["count"] == 0:
             return
         valid = out["valid"].astype(bool)

@@ -126,6 +126,20 @@ struct fcp_ctx {
     double prof_flops = 0, prof_bytes = 0;
     struct ProfRec { int m, cout, cin, k, stride, tc; };
     std::vector<ProfRec> prof_recs;     // one per event pair (FCP_TRACE=1 prints a per-shape table)
+    // per-stage event pairs (fcp_profile_stages): detect net, detect post, enhance, align, parse net, parse tail, gather, ingest
+    struct StageRec { int stage; cudaEvent_t a, b; };
+    std::vector<StageRec> stage_recs;
+    size_t stage_used = 0;
+    // RRDBNet stage of fcp_pipeline (fcp_set_enhance): < 0 = off, else the min_face_factor threshold of rrdb.py:141
+    float enh_threshold = -1.f;
+    // multi-GPU metadata all-gather (comm.cu): NCCL communicator + side stream; gather_out != nullptr makes fcp_pipeline
+    // pack and all-gather its face records on comm_stream while the parser runs
+    void* nccl_comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t comm_ready = nullptr, comm_done = nullptr;
+    double* gather_out = nullptr; int gather_cap = 0, gather_base = 0;
+    double* gather_send = nullptr; size_t gather_send_cap = 0;
     // fcp_pipeline with HOST images: the batch is copied H2D per detector micro-batch on a second stream, one micro-batch
     // ahead of the compute stream (the hook runs at the top of every detector micro-batch)
     cudaStream_t copy_stream = nullptr;
@@ -136,6 +150,18 @@ struct fcp_ctx {
 namespace fcp {
 
 int fail(fcp_ctx* ctx, int code, const std::string& msg);
+
+enum Stage { ST_DETECT_NET = 0, ST_DETECT_POST, ST_ENHANCE, ST_ALIGN, ST_PARSE_NET, ST_PARSE_TAIL, ST_GATHER, ST_INGEST, ST_COUNT };
+// event pair around a stage while profiling is on (no-op otherwise); the pair is recorded on `stream` (default: ctx->stream)
+struct StageScope {
+    StageScope(fcp_ctx* ctx, int stage, cudaStream_t stream = nullptr, bool use_stream = false);
+    ~StageScope();
+    fcp_ctx* ctx; cudaStream_t stream; cudaEvent_t end = nullptr;
+};
+// packs this rank's face records and all-gathers them on the communicator's side stream (comm.cu); no-op without a comm
+int gather_meta_async(fcp_ctx* ctx, const float* landmarks, const int32_t* face_img, const double* matrices, const uint8_t* valid,
+                      const int32_t* face_count, int cap, int index_base, double* out_records);
+int gather_meta_join(fcp_ctx* ctx);
 
 #define FCP_CUDA(ctx, expr)                                                                            \
     do {                                                                                               \
@@ -181,6 +207,8 @@ int launch_stem_rows(fcp_ctx* ctx, const void* src, int mode, int n, int h, int 
 // conv 3x3/s1 with Cin=3 (RRDB conv_first): f32 NCHW input scaled by in_scale, + bias
 int launch_conv3_first(fcp_ctx* ctx, const float* src_nchw, float in_scale, int n, int h, int w, const float* w_kn,
                        const float* shift, Tensor out);
+// same, input = u8 NHWC RGB (the value / 255, like rrdb.py:142 on a 0..255 float image)
+int launch_conv3_first_u8(fcp_ctx* ctx, const uint8_t* src_nhwc, int n, int h, int w, const float* w_kn, const float* shift, Tensor out);
 int launch_maxpool3s2(fcp_ctx* ctx, Tensor in, Tensor out);
 int launch_global_avgpool(fcp_ctx* ctx, Tensor in, float* out_nc);                     // out[n][c] = mean_hw
 // out[n][co] = act((sum_ci in[n][ci] * w[ci][co]) * scale[co] + shift[co])           (1x1 conv on a pooled vector)
@@ -202,6 +230,13 @@ int launch_det_post(fcp_ctx* ctx, const float* const* level_ptrs, const float* h
 // faces[f][16] records -> landmarks [f][10] (minus (left, top) of paddings[img]), boxes, scores, anchors
 int launch_unpack_faces(fcp_ctx* ctx, const float* faces, const int32_t* face_img, const int32_t* face_count, int cap,
                         const int32_t* paddings, float* landmarks, float* boxes, float* scores, int32_t* anchors);
+
+// RRDBNet.predict gate (rrdb.py:124-141) on the un-padded landmarks; gate[i] = 1: enhance image i
+int launch_enhance_gate(fcp_ctx* ctx, const float* landmarks, const int32_t* face_img, const int32_t* face_count, int cap, int n,
+                        int h, int w, float threshold, uint8_t* gate);
+// [cap + 1][20] float64 metadata records of the multi-GPU all-gather (slot cap: face count)
+int launch_pack_records(fcp_ctx* ctx, const float* landmarks, const int32_t* face_img, const double* matrices, const uint8_t* valid,
+                        const int32_t* face_count, int cap, int index_base, double* records, cudaStream_t stream);
 
 // align (align.cu)
 int launch_solve(fcp_ctx* ctx, const float* landmarks, const int32_t* face_count_dev, int f, const float* target,
@@ -226,6 +261,8 @@ int launch_nhwc_to_nchw(fcp_ctx* ctx, const float* in, int n, int h, int w, int 
 
 // enhance tail: conv_last output [n,4h,4w,3(+pad)] -> bicubic x0.25 -> clamp*255 round, written NCHW f32 [3,h,w]
 int launch_rrdb_tail(fcp_ctx* ctx, Tensor x4, float* out_nchw, int h, int w);
+// same, written as u8 NHWC [n,h,w,3] (round(clamp(x,0,1)*255) is integral: the reference's as_numpy cast is exact)
+int launch_rrdb_tail_u8(fcp_ctx* ctx, Tensor x4, uint8_t* out_nhwc, int h, int w);
 
 // model graphs (runtime.cu)
 int finalize_retinaface(fcp_ctx* ctx);

@@ -83,6 +83,7 @@ struct alignas(64) TcParams {
     float post_scale2; const float* res3; int res3_cs, res3_co;
     int ablate;                                // FCP_TC_ABLATE bit mask, measurement only (results are WRONG with bits 1/2):
                                                //   1 skip the w_lo loads (L2->SM / smem-write traffic probe), 2 skip the bulk stores,
+                                               //   4 converters skip the fp16 split arithmetic (MODE 1),
                                                //   16 back-off in the drain warps' d_full wait
     long long* dbg;                            // FCP_EXP_TIMELINE: clock64 stamps of CTA 0, [g][16]
 };
@@ -494,6 +495,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     for (int hf = 0; hf < 2; ++hf) {
                         if (hf == 0 || two) {
                             uint32_t hi[16], lo[16];
+                            if (p.ablate & 4) {                           // measurement only: no split arithmetic
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) { hi[j] = __float_as_uint(x[32 * hf + 2 * j]) & 0x3FFF3FFFu; lo[j] = 0; }
+                            } else
 #pragma unroll
                             for (int j = 0; j < 16; ++j) {
                                 const float a0 = x[32 * hf + 2 * j] * sc, a1 = x[32 * hf + 2 * j + 1] * sc;
@@ -559,7 +564,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             //      previous tile's bulk stores have released the slab (waited for by the threads that issued them, published
             //      by one group barrier), and the residual chunks (128 pixels x 32 channels each) stream into the slab while
             //      the K loop runs.
-            auto after_first_kblock = [&]() {
+            // Tiles with a short K loop (<= 4 K-blocks, e.g. the bottleneck 1x1 convs) cannot hide the residual's HBM latency
+            // behind the K-blocks that follow the first drain, so they decode and prefetch at the TOP of the tile: the
+            // thread that issued the previous tile's store of chunk q waits for that store to have read the slab and
+            // re-fills chunk q by TMA (nobody else touches the slab between the pre-store barrier and the next phase 1).
+            const bool early = kblocks <= 4 && (!has_res || p.res_tma);
+            auto decode_and_fetch = [&]() {
                 const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
                 img = m_tile / tiles_per_img;
                 const int rem = m_tile - img * tiles_per_img;
@@ -567,15 +577,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 n0 = n_tile * BN + half * HALF;                               // first channel of this group
                 if (lane < HALF / 4)
                     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(par + lane * 16), "l"(p.shift + n0 + lane * 4) : "memory");
+                if (has_res && p.res_tma && dma) {
+                    bulk_wait_read();
+                    mbar_expect_tx(rbar, C::CHUNK_BYTES);
+                    tma_load_4d(slab_all + (half * CHUNKS + quarter) * C::CHUNK_BYTES, &p.tmRes, rbar, n0 + quarter * 32, wo0, ho0, img);
+                }
+            };
+            if (early) decode_and_fetch();
+            auto after_first_kblock = [&]() {
+                if (!early) decode_and_fetch();
                 if (dma) bulk_wait_read();
                 group_sync();
-                if (!has_res) return;
-                if (p.res_tma) {
-                    if (dma) {
-                        mbar_expect_tx(rbar, C::CHUNK_BYTES);
-                        tma_load_4d(slab_all + (half * CHUNKS + quarter) * C::CHUNK_BYTES, &p.tmRes, rbar, n0 + quarter * 32, wo0, ho0, img);
-                    }
-                } else {
+                if (has_res && !p.res_tma) {
                     // cp.async fallback (resized or unaligned residual): HALF/4 lanes cover one pixel, RR pixels per instruction
                     constexpr int RL = HALF / 4, RR = 32 / RL;
                     const int pc = lane % RL, rrow = lane / RL;               // 16-byte piece within the row

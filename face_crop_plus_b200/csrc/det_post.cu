@@ -273,6 +273,74 @@ __global__ void unpack_faces_kernel(const float* __restrict__ faces, const int* 
     if (anchors) anchors[i] = __float_as_int(r[1]);
 }
 
+// numpy's pairwise summation of a float32 vector (loops_utils.h.src, PW_BLOCKSIZE 128): what `ndarray.mean()` of
+// rrdb.py:141 accumulates with.  v(i) returns element i.
+template <class F>
+__device__ float np_pairwise_sum(F v, int lo, int n) {
+    if (n < 8) {
+        float res = 0.f;
+        for (int i = 0; i < n; ++i) res = __fadd_rn(res, v(lo + i));
+        return res;
+    }
+    if (n <= 128) {
+        float r[8];
+        for (int j = 0; j < 8; ++j) r[j] = v(lo + j);
+        int i = 8;
+        for (; i < n - (n % 8); i += 8)
+            for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], v(lo + i + j));
+        float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                              __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+        for (; i < n; ++i) res = __fadd_rn(res, v(lo + i));
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return __fadd_rn(np_pairwise_sum(v, lo, n2), np_pairwise_sum(v, lo + n2, n - n2));
+}
+
+// RRDBNet.predict's per-image gate (rrdb.py:124-141): enhance image i iff mean_f((x4-x0)*(y4-y0) / (H*W)) <= threshold over
+// its faces, all in float32 like numpy; images without faces are skipped.  faces are stored in image order.
+__global__ void enhance_gate_kernel(const float* __restrict__ lms, const int* __restrict__ face_img,
+                                    const int* __restrict__ face_count, int cap, int n, float hw, float thr,
+                                    unsigned char* __restrict__ gate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int f = min(*face_count, cap);
+    int a = 0, b = f;                                     // [lo, hi) = faces of image i (face_img is ascending)
+    while (a < b) { const int m = (a + b) >> 1; if (face_img[m] < i) a = m + 1; else b = m; }
+    const int lo = a;
+    b = f;
+    while (a < b) { const int m = (a + b) >> 1; if (face_img[m] <= i) a = m + 1; else b = m; }
+    const int hi = a;
+    if (hi == lo) { gate[i] = 0; return; }                // no landmarks found: the image is skipped (rrdb.py:133-135)
+    auto factor = [&](int k) {
+        const float* l = lms + (size_t)k * 10;
+        const float w = __fsub_rn(l[8], l[0]), h = __fsub_rn(l[9], l[1]);
+        return __fdiv_rn(__fmul_rn(w, h), hw);
+    };
+    const int cnt = hi - lo;
+    const float mean = __fdiv_rn(np_pairwise_sum(factor, lo, cnt), (float)cnt);
+    gate[i] = mean <= thr ? 1 : 0;
+}
+
+// per-face metadata record of the all-gather (distributed.py RECORD = 20 float64): landmarks[10], GLOBAL image index,
+// matrix[6], valid, 2 reserved; slot `cap` carries the face count in column 0
+__global__ void pack_records_kernel(const float* __restrict__ lms, const int* __restrict__ face_img, const double* __restrict__ mats,
+                                    const unsigned char* __restrict__ valid, const int* __restrict__ face_count, int cap,
+                                    int index_base, double* __restrict__ rec) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > cap) return;
+    double* r = rec + (size_t)i * 20;
+    const int f = min(*face_count, cap);
+    if (i == cap) { r[0] = (double)f; for (int k = 1; k < 20; ++k) r[k] = 0.0; return; }
+    if (i >= f) { for (int k = 0; k < 20; ++k) r[k] = 0.0; return; }
+    for (int k = 0; k < 10; ++k) r[k] = (double)lms[(size_t)i * 10 + k];
+    r[10] = (double)(face_img[i] + index_base);
+    for (int k = 0; k < 6; ++k) r[11 + k] = mats ? mats[(size_t)i * 6 + k] : 0.0;
+    r[17] = valid ? (double)valid[i] : 1.0;
+    r[18] = r[19] = 0.0;
+}
+
 DetSrc make_src(const float* const* level_ptrs, const float* flat, int h, int w) {
     DetSrc s{};
     int acc = 0;
@@ -314,6 +382,21 @@ int launch_unpack_faces(fcp_ctx* ctx, const float* faces, const int32_t* face_im
     if (cap == 0) return FCP_OK;
     unpack_faces_kernel<<<(cap + 127) / 128, 128, 0, ctx->stream>>>(faces, face_img, face_count, cap, paddings, landmarks,
                                                                   boxes, scores, anchors);
+    FCP_KERNEL_CHECK(ctx);
+    return FCP_OK;
+}
+
+int launch_enhance_gate(fcp_ctx* ctx, const float* landmarks, const int32_t* face_img, const int32_t* face_count, int cap, int n,
+                        int h, int w, float threshold, uint8_t* gate) {
+    if (n == 0) return FCP_OK;
+    enhance_gate_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(landmarks, face_img, face_count, cap, n, (float)(h * w), threshold, gate);
+    FCP_KERNEL_CHECK(ctx);
+    return FCP_OK;
+}
+
+int launch_pack_records(fcp_ctx* ctx, const float* landmarks, const int32_t* face_img, const double* matrices, const uint8_t* valid,
+                        const int32_t* face_count, int cap, int index_base, double* records, cudaStream_t stream) {
+    pack_records_kernel<<<(cap + 1 + 127) / 128, 128, 0, stream>>>(landmarks, face_img, matrices, valid, face_count, cap, index_base, records);
     FCP_KERNEL_CHECK(ctx);
     return FCP_OK;
 }

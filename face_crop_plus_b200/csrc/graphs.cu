@@ -362,12 +362,13 @@ int finalize_rrdbnet(fcp_ctx* ctx) {
     return FCP_OK;
 }
 
-// RRDBNet.forward (rrdb.py:64-81) on nb images [nb,3,h,w] NCHW scaled by 1/in_div; result x4 = [nb,4h,4w,3] (cs 4)
-static int rrdbnet_forward(Exec& ex, const float* x_nchw, float in_div, int nb, int h, int w, Tensor& x4) {
+// RRDBNet.forward (rrdb.py:64-81) on nb images; `fill_first(first)` runs conv_first of the nb inputs into
+// first = [nb,h,w,64] (f32 NCHW / in_div or u8 NHWC / 255 sources); result x4 = [nb,4h,4w,3] (cs 4)
+static int rrdbnet_forward(Exec& ex, const std::function<int(Tensor)>& fill_first, int nb, int h, int w, Tensor& x4) {
     const ConvWeights* cf = ex.W("conv_first");
     if (!cf) return ex.status;
     Tensor first = ex.alloc(nb, h, w, 64);
-    if (ex.ok() && !ex.dry) ex.status = launch_conv3_first(ex.ctx, x_nchw, in_div, nb, h, w, cf->w_kn, cf->shift, first);
+    if (ex.ok() && !ex.dry) ex.status = fill_first(first);
     // three rotating 192-channel slabs [x | x1 | x2 | x3 | x4]: the dense concatenations of
     // ResidualDenseBlock_5C (_layers.py:179-186) are channel-prefix views of one slab
     Tensor slab[3];
@@ -473,9 +474,13 @@ static int detect_core(fcp_ctx* ctx, const uint8_t* images, int n, int h, int w,
         ctx->arena.reset();
         Exec ex{ctx, model, false};
         Tensor lvl[3];
-        status = retinaface_forward(ex, images + (size_t)b0 * h * w * 3, nb, h, w, lvl);
+        {
+            StageScope st(ctx, ST_DETECT_NET);
+            status = retinaface_forward(ex, images + (size_t)b0 * h * w * 3, nb, h, w, lvl);
+        }
         if (status != FCP_OK) break;
         const float* ptrs[3] = {lvl[0].p, lvl[1].p, lvl[2].p};
+        StageScope st(ctx, ST_DETECT_POST);
         if (heads_out) status = launch_heads_to_flat(ctx, ptrs, nb, h, w, heads_out + (size_t)b0 * A * 16);
         else status = launch_det_post(ctx, ptrs, nullptr, nb, b0, h, w, vis, nms, strategy, max_faces, rec, keys, supp,
                                       counts, counts + mb, faces, face_img, face_count);
@@ -509,7 +514,11 @@ static int parse_core(fcp_ctx* ctx, const uint8_t* crops, int f, int h, int w, u
         ctx->arena.reset();
         Exec ex{ctx, model, false};
         Tensor logits;
-        FCP_TRY(graph(ex, crops + (size_t)b0 * h * w * 3, nb, logits));
+        {
+            StageScope st(ctx, ST_PARSE_NET);
+            FCP_TRY(graph(ex, crops + (size_t)b0 * h * w * 3, nb, logits));
+        }
+        StageScope st(ctx, ST_PARSE_TAIL);
         if (logits_nchw)
             FCP_TRY(launch_nhwc_to_nchw(ctx, logits.p, nb, 64, 64, 19, logits.cs, logits_nchw + (size_t)b0 * 19 * 64 * 64));
         if (labels || hist)
@@ -527,6 +536,7 @@ static int align_core(fcp_ctx* ctx, const uint8_t* images, int n, int h, int w, 
     if (f == 0) return FCP_OK;
     double* inv = nullptr;
     FCP_CUDA(ctx, cudaMallocAsync(&inv, sizeof(double) * 6 * f, ctx->stream));
+    StageScope st(ctx, ST_ALIGN);
     int s = launch_solve(ctx, landmarks, face_count_dev, f, target, skew, matrices, inv, valid);
     if (s == FCP_OK)
         s = launch_warp(ctx, images, n, h, w, ptrs, hs, ws, paddings, indices, face_count_dev, f, inv, valid, out_w, out_h, border, crops);
@@ -792,20 +802,59 @@ int fcp_masks(fcp_ctx* ctx, const uint8_t* labels, int f, int h, int w, const ui
     return FCP_OK;
 }
 
-static int enhance_core(fcp_ctx* ctx, const float* x, float in_div, int n, int h, int w, const uint8_t* gate_host,
-                        float* out_x4_nchw, float* out_x1_nchw) {
+// RRDBNet over the gated images of a batch.  Sources: f32 NCHW `x` (value / in_div) or u8 NHWC `x_u8` (value / 255);
+// sinks: the raw x4 output (f32 NCHW), the predict() result bicubic(x4, 1/4) -> clamp -> *255 -> round as f32 NCHW, or as
+// u8 NHWC `out_u8[job]` (densely packed: one h*w*3 image per gated job, in image order).
+// rrdb.py:124 enhances image by image to bound the reference's memory; the images are independent, so several small ones
+// share a launch here (fills the 148 SMs: a 256x256 image is only 512 tiles per conv).
+static int enhance_core(fcp_ctx* ctx, const float* x, float in_div, const uint8_t* x_u8, int n, int h, int w,
+                        const uint8_t* gate_host, float* out_x4_nchw, float* out_x1_nchw, uint8_t* out_u8) {
     Model* model = &ctx->models[FCP_MODEL_RRDBNET];
+    std::vector<int> jobs;
+    for (int i = 0; i < n; ++i)
+        if (!gate_host || gate_host[i]) jobs.push_back(i);
+    if (jobs.empty()) return FCP_OK;
+    const long long px = (long long)h * w;
+    int nb = (int)std::max(1LL, std::min<long long>(8, (1LL << 20) / std::max(1LL, px)));
+    if (const char* e = getenv("FCP_ENH_BATCH")) nb = std::max(1, atoi(e));
+    nb = std::min<int>(nb, (int)jobs.size());
+    const ConvWeights* cf = nullptr;
+    {
+        auto it = model->conv.find("conv_first");
+        if (it == model->conv.end()) return fail(ctx, FCP_ERR_STATE, "conv not finalized: conv_first");
+        cf = &it->second;
+    }
     std::vector<std::function<int(Exec&)>> plans;
-    plans.push_back([=](Exec& ex) { Tensor t; return rrdbnet_forward(ex, nullptr, in_div, 1, h, w, t); });
+    auto noop = [](Tensor) { return FCP_OK; };
+    for (int b : {nb, (int)(jobs.size() % nb)})
+        if (b > 0) plans.push_back([=](Exec& ex) { Tensor t; return rrdbnet_forward(ex, noop, b, h, w, t); });
     FCP_TRY(plan_reserve(ctx, model, plans));
-    for (int i = 0; i < n; ++i) {                       // one image at a time, like rrdb.py:124-144
-        if (gate_host && !gate_host[i]) continue;
+    for (size_t j0 = 0; j0 < jobs.size(); j0 += nb) {
+        const int b = (int)std::min<size_t>(nb, jobs.size() - j0);
         ctx->arena.reset();
         Exec ex{ctx, model, false};
         Tensor x4;
-        FCP_TRY(rrdbnet_forward(ex, x + (size_t)i * 3 * h * w, in_div, 1, h, w, x4));
-        if (out_x4_nchw) FCP_TRY(launch_nhwc_to_nchw(ctx, x4.p, 1, 4 * h, 4 * w, 3, x4.cs, out_x4_nchw + (size_t)i * 3 * 16 * h * w));
-        if (out_x1_nchw) FCP_TRY(launch_rrdb_tail(ctx, x4, out_x1_nchw + (size_t)i * 3 * h * w, h, w));
+        auto fill = [&](Tensor first) -> int {
+            for (int k = 0; k < b; ++k) {
+                const int i = jobs[j0 + k];
+                Tensor f1 = first;
+                f1.n = 1;
+                f1.p = first.p + (size_t)k * px * first.cs;
+                if (x_u8) FCP_TRY(launch_conv3_first_u8(ctx, x_u8 + (size_t)i * px * 3, 1, h, w, cf->w_kn, cf->shift, f1));
+                else FCP_TRY(launch_conv3_first(ctx, x + (size_t)i * 3 * px, in_div, 1, h, w, cf->w_kn, cf->shift, f1));
+            }
+            return FCP_OK;
+        };
+        FCP_TRY(rrdbnet_forward(ex, fill, b, h, w, x4));
+        for (int k = 0; k < b; ++k) {
+            const int i = jobs[j0 + k];
+            Tensor x1 = x4;
+            x1.n = 1;
+            x1.p = x4.p + (size_t)k * 16 * px * x4.cs;
+            if (out_x4_nchw) FCP_TRY(launch_nhwc_to_nchw(ctx, x1.p, 1, 4 * h, 4 * w, 3, x1.cs, out_x4_nchw + (size_t)i * 3 * 16 * px));
+            if (out_x1_nchw) FCP_TRY(launch_rrdb_tail(ctx, x1, out_x1_nchw + (size_t)i * 3 * px, h, w));
+            if (out_u8) FCP_TRY(launch_rrdb_tail_u8(ctx, x1, out_u8 + (j0 + k) * px * 3, h, w));
+        }
     }
     return FCP_OK;
 }
@@ -853,17 +902,63 @@ int fcp_enhance(fcp_ctx* ctx, float* images, int n, int h, int w, const uint8_t*
     }
     if (is_device_ptr(images)) {
         // in-place on device: the tail writes image i only after the whole graph of image i has consumed it
-        FCP_TRY(enhance_core(ctx, images, 255.f, n, h, w, gate.data(), nullptr, images));
+        FCP_TRY(enhance_core(ctx, images, 255.f, nullptr, n, h, w, gate.data(), nullptr, images, nullptr));
     } else {
         float* dev;
         FCP_CUDA(ctx, cudaMallocAsync(&dev, bytes, ctx->stream));
         FCP_CUDA(ctx, cudaMemcpyAsync(dev, images, bytes, cudaMemcpyHostToDevice, ctx->stream));
-        int s = enhance_core(ctx, dev, 255.f, n, h, w, gate.data(), nullptr, dev);
+        int s = enhance_core(ctx, dev, 255.f, nullptr, n, h, w, gate.data(), nullptr, dev, nullptr);
         if (s == FCP_OK && cudaMemcpyAsync(images, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
             s = fail(ctx, FCP_ERR_CUDA, "D2H copy failed");
         cudaFreeAsync(dev, ctx->stream);
         FCP_TRY(s);
     }
+    FCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FCP_OK;
+}
+
+int fcp_enhance_u8(fcp_ctx* ctx, uint8_t* images, int n, int h, int w, const uint8_t* do_enhance) {
+    FCP_TRY(need_model(ctx, FCP_MODEL_RRDBNET));
+    if (!images || n < 1 || h < 1 || w < 1) return fail(ctx, FCP_ERR_INVALID, "fcp_enhance_u8: bad argument");
+    const size_t img_bytes = (size_t)h * w * 3;
+    std::vector<uint8_t> gate(n, 1);
+    if (do_enhance) {
+        if (is_device_ptr(do_enhance)) FCP_CUDA(ctx, cudaMemcpy(gate.data(), do_enhance, n, cudaMemcpyDeviceToHost));
+        else gate.assign(do_enhance, do_enhance + n);
+    }
+    int jobs = 0;
+    for (uint8_t g : gate) jobs += g != 0;
+    if (jobs == 0) return FCP_OK;
+    DevIn in;
+    FCP_TRY(in.init(ctx, images, img_bytes * n));
+    uint8_t* dense = nullptr;
+    FCP_CUDA(ctx, cudaMallocAsync(&dense, img_bytes * jobs, ctx->stream));
+    int s = enhance_core(ctx, nullptr, 255.f, in.as<uint8_t>(), n, h, w, gate.data(), nullptr, nullptr, dense);
+    const bool dev = is_device_ptr(images);
+    for (int i = 0, j = 0; i < n && s == FCP_OK; ++i)
+        if (gate[i] && cudaMemcpyAsync(images + (size_t)i * img_bytes, dense + (size_t)(j++) * img_bytes, img_bytes,
+                                       dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+            s = fail(ctx, FCP_ERR_CUDA, "fcp_enhance_u8: result copy failed");
+    cudaFreeAsync(dense, ctx->stream);
+    FCP_TRY(s);
+    FCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FCP_OK;
+}
+
+int fcp_enhance_gate(fcp_ctx* ctx, const float* landmarks, const int32_t* indices, int f, int n, int h, int w,
+                     float min_face_factor, uint8_t* out_gate) {
+    if (!ctx || f < 0 || n < 0 || !out_gate || (f && (!landmarks || !indices))) return fail(ctx, FCP_ERR_INVALID, "fcp_enhance_gate: bad argument");
+    FCP_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n == 0) return FCP_OK;
+    DevIn lms, idx, cnt;
+    FCP_TRY(lms.init(ctx, landmarks, sizeof(float) * 10 * f));
+    FCP_TRY(idx.init(ctx, indices, sizeof(int32_t) * f));
+    const int32_t c = f;
+    FCP_TRY(cnt.init(ctx, &c, sizeof c));
+    DevOut g;
+    FCP_TRY(g.init(ctx, out_gate, n));
+    FCP_TRY(launch_enhance_gate(ctx, lms.as<float>(), idx.as<int32_t>(), cnt.as<int32_t>(), f, n, h, w, min_face_factor, g.as<uint8_t>()));
+    FCP_TRY(g.flush());
     FCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FCP_OK;
 }
@@ -875,7 +970,7 @@ int fcp_enhance_forward(fcp_ctx* ctx, const float* x, int n, int h, int w, float
     FCP_TRY(in.init(ctx, x, sizeof(float) * 3 * h * w * (size_t)n));
     DevOut o;
     FCP_TRY(o.init(ctx, out, sizeof(float) * 3 * 16 * h * w * (size_t)n));
-    FCP_TRY(enhance_core(ctx, in.as<float>(), 1.f, n, h, w, nullptr, o.as<float>(), nullptr));
+    FCP_TRY(enhance_core(ctx, in.as<float>(), 1.f, nullptr, n, h, w, nullptr, o.as<float>(), nullptr, nullptr));
     FCP_TRY(o.flush());
     FCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FCP_OK;
@@ -887,21 +982,47 @@ int fcp_pipeline(fcp_ctx* ctx, const uint8_t* images, int n, int h, int w, const
                  uint8_t* out_crops, double* out_matrices, uint8_t* out_valid, uint8_t* out_labels, int32_t* out_hist) {
     FCP_TRY(need_model(ctx, FCP_MODEL_RETINAFACE));
     const bool do_parse = out_labels || out_hist;
+    const bool do_enhance = ctx->enh_threshold >= 0.f;
     if (do_parse) FCP_TRY(need_model(ctx, FCP_MODEL_BISENET));
+    if (do_enhance) FCP_TRY(need_model(ctx, FCP_MODEL_RRDBNET));
     if (!images || n < 1 || max_faces < 1 || !out_count || !target || !out_crops || strategy < 0 || strategy > 2 ||
         border_mode < 0 || border_mode > 4)
         return fail(ctx, FCP_ERR_INVALID, "fcp_pipeline: bad argument");
     DevIn pad, tgt;
     FCP_TRY(pad.init(ctx, paddings, sizeof(int32_t) * 4 * n));
     FCP_TRY(tgt.init(ctx, target, sizeof(float) * 10));
+    const size_t img_bytes = (size_t)h * w * 3;
+    // every stream-ordered temporary of the call; released (and the micro-batch hook cleared) on EVERY exit path
+    struct Temps {
+        fcp_ctx* ctx;
+        std::vector<void*> ptrs;
+        bool staged = false;
+        ~Temps() {
+            ctx->on_microbatch = nullptr;
+            if (staged && ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);   // no copy may outlive its buffer
+            for (void* p : ptrs) cudaFreeAsync(p, ctx->stream);
+        }
+        int alloc(void** p, size_t bytes) {
+            if (cudaMallocAsync(p, bytes ? bytes : 1, ctx->stream) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(ctx, FCP_ERR_CUDA, "fcp_pipeline: out of device memory (" + std::to_string(bytes >> 20) + " MiB)");
+            }
+            ptrs.push_back(*p);
+            return FCP_OK;
+        }
+    } tmp{ctx};
+    float* faces; int32_t* face_img; int32_t* face_count; uint8_t* gate = nullptr;
+    FCP_TRY(tmp.alloc((void**)&faces, sizeof(float) * 16 * max_faces));
+    FCP_TRY(tmp.alloc((void**)&face_img, sizeof(int32_t) * max_faces));
+    FCP_TRY(tmp.alloc((void**)&face_count, sizeof(int32_t)));
+    if (do_enhance) FCP_TRY(tmp.alloc((void**)&gate, n));
     // Images in host memory are copied per detector micro-batch on a second stream, one micro-batch ahead of the compute
     // stream, so that (with pinned buffers) only the first micro-batch's copy is exposed.
     const uint8_t* dimg = images;
-    uint8_t* staged = nullptr;
-    const size_t img_bytes = (size_t)h * w * 3;
     if (!is_device_ptr(images)) {
+        uint8_t* staged = nullptr;
         const int mb = std::min(ctx->det_mb, n), chunks = (n + mb - 1) / mb;
-        FCP_CUDA(ctx, cudaMallocAsync(&staged, img_bytes * n, ctx->stream));
+        FCP_TRY(tmp.alloc((void**)&staged, img_bytes * n));
         if (!ctx->copy_stream) FCP_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         while ((int)ctx->copy_events.size() < chunks + 1) {
             cudaEvent_t e;
@@ -910,6 +1031,7 @@ int fcp_pipeline(fcp_ctx* ctx, const uint8_t* images, int n, int h, int w, const
         }
         FCP_CUDA(ctx, cudaEventRecord(ctx->copy_events[chunks], ctx->stream));              // the allocation is stream-ordered
         FCP_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_events[chunks], 0));
+        tmp.staged = true;
         auto issue = [ctx, images, staged, img_bytes, mb, n, chunks](int c) -> int {
             if (c >= chunks) return FCP_OK;
             const size_t off = (size_t)c * mb * img_bytes, bytes = (size_t)std::min(mb, n - c * mb) * img_bytes;
@@ -926,60 +1048,77 @@ int fcp_pipeline(fcp_ctx* ctx, const uint8_t* images, int n, int h, int w, const
         };
         dimg = staged;
     }
-    float* faces; int32_t* face_img; int32_t* face_count;
-    FCP_CUDA(ctx, cudaMallocAsync(&faces, sizeof(float) * 16 * max_faces, ctx->stream));
-    FCP_CUDA(ctx, cudaMallocAsync(&face_img, sizeof(int32_t) * max_faces, ctx->stream));
-    FCP_CUDA(ctx, cudaMallocAsync(&face_count, sizeof(int32_t), ctx->stream));
-    auto cleanup = [&]() {
-        cudaFreeAsync(faces, ctx->stream); cudaFreeAsync(face_img, ctx->stream); cudaFreeAsync(face_count, ctx->stream);
-        if (staged) { cudaStreamSynchronize(ctx->copy_stream); cudaFreeAsync(staged, ctx->stream); }   // no copy may outlive the buffer
-    };
-    int s = detect_core(ctx, dimg, n, h, w, vis_threshold, nms_threshold, strategy, max_faces, faces, face_img,
-                        face_count, nullptr);
+    FCP_TRY(detect_core(ctx, dimg, n, h, w, vis_threshold, nms_threshold, strategy, max_faces, faces, face_img, face_count, nullptr));
     ctx->on_microbatch = nullptr;
-    if (s != FCP_OK) { cleanup(); return s; }
-    // landmark un-pad (cropper.py:822) happens while unpacking the face records
+    // landmark un-pad (cropper.py:822) happens while unpacking the face records; the enhancement gate (rrdb.py:124-141)
+    // is evaluated on the device from the un-padded landmarks and comes back with the face count in the one host sync
     DevOut lms, crops, mats, valid, lab, hist;
     int32_t count = 0;
-    s = lms.init(ctx, out_landmarks, sizeof(float) * 10 * max_faces, true);
-    if (s == FCP_OK) s = launch_unpack_faces(ctx, faces, face_img, face_count, max_faces, pad.as<int32_t>(), lms.as<float>(), nullptr, nullptr, nullptr);
-    if (s == FCP_OK && cudaMemcpyAsync(&count, face_count, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
-        s = fail(ctx, FCP_ERR_CUDA, "count D2H failed");
-    if (s == FCP_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) s = fail(ctx, FCP_ERR_CUDA, "sync failed");
-    if (s != FCP_OK) { cleanup(); return s; }
+    std::vector<uint8_t> gate_host(do_enhance ? n : 0, 0);
+    FCP_TRY(lms.init(ctx, out_landmarks, sizeof(float) * 10 * max_faces, true));
+    FCP_TRY(launch_unpack_faces(ctx, faces, face_img, face_count, max_faces, pad.as<int32_t>(), lms.as<float>(), nullptr, nullptr, nullptr));
+    if (do_enhance) {
+        FCP_TRY(launch_enhance_gate(ctx, lms.as<float>(), face_img, face_count, max_faces, n, h, w, ctx->enh_threshold, gate));
+        FCP_CUDA(ctx, cudaMemcpyAsync(gate_host.data(), gate, n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    FCP_CUDA(ctx, cudaMemcpyAsync(&count, face_count, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    FCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const int f = std::min(count, max_faces);
     if (f > 0) {
-        s = crops.init(ctx, out_crops, (size_t)f * out_h * out_w * 3);
-        if (s == FCP_OK) s = mats.init(ctx, out_matrices, sizeof(double) * 6 * f, true);
-        if (s == FCP_OK) s = valid.init(ctx, out_valid, f, true);
-        if (s == FCP_OK)
-            s = align_core(ctx, dimg, n, h, w, nullptr, nullptr, nullptr, pad.as<int32_t>(), face_img, nullptr,
-                           lms.as<float>(), f, tgt.as<float>(), out_w, out_h, border_mode, allow_skew, crops.as<uint8_t>(),
-                           mats.as<double>(), valid.as<uint8_t>());
-        if (s == FCP_OK && do_parse) {
-            s = lab.init(ctx, out_labels, (size_t)f * out_h * out_w);
-            if (s == FCP_OK) s = hist.init(ctx, out_hist, sizeof(int32_t) * 19 * f);
-            if (s == FCP_OK) s = parse_core(ctx, crops.as<uint8_t>(), f, out_h, out_w, lab.as<uint8_t>(), hist.as<int32_t>(), nullptr);
+        // ---- enhance (rrdb.py:83-146, cropper.py:833-836): the gated images are rebuilt as u8 on the device; the warp
+        //      reads them through a per-image pointer table, the caller's batch is never modified
+        const uint8_t* const* ptr_table = nullptr; const int32_t* hs_dev = nullptr; const int32_t* ws_dev = nullptr;
+        int n_gated = 0;
+        for (uint8_t g : gate_host) n_gated += g;
+        if (n_gated > 0) {
+            StageScope st(ctx, ST_ENHANCE);
+            uint8_t* enhanced = nullptr; void* table = nullptr; int32_t* dims = nullptr;
+            FCP_TRY(tmp.alloc((void**)&enhanced, img_bytes * n_gated));
+            FCP_TRY(tmp.alloc(&table, sizeof(void*) * n));
+            FCP_TRY(tmp.alloc((void**)&dims, sizeof(int32_t) * 2 * n));
+            FCP_TRY(enhance_core(ctx, nullptr, 255.f, dimg, n, h, w, gate_host.data(), nullptr, nullptr, enhanced));
+            std::vector<const uint8_t*> ptrs(n);
+            std::vector<int32_t> hw(2 * n);
+            for (int i = 0, j = 0; i < n; ++i) {
+                ptrs[i] = gate_host[i] ? enhanced + (size_t)(j++) * img_bytes : dimg + (size_t)i * img_bytes;
+                hw[i] = h; hw[n + i] = w;
+            }
+            FCP_CUDA(ctx, cudaMemcpyAsync(table, ptrs.data(), sizeof(void*) * n, cudaMemcpyHostToDevice, ctx->stream));
+            FCP_CUDA(ctx, cudaMemcpyAsync(dims, hw.data(), sizeof(int32_t) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
+            FCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));                            // the host vectors die with this scope
+            ptr_table = static_cast<const uint8_t* const*>(table); hs_dev = dims; ws_dev = dims + n;
         }
-        if (s == FCP_OK) s = lms.flush(sizeof(float) * 10 * f);
-        if (s == FCP_OK) s = crops.flush();
-        if (s == FCP_OK) s = mats.flush();
-        if (s == FCP_OK) s = valid.flush();
-        if (s == FCP_OK) s = lab.flush();
-        if (s == FCP_OK) s = hist.flush();
-        if (s == FCP_OK && out_indices &&
-            cudaMemcpyAsync(out_indices, face_img, sizeof(int32_t) * f,
-                            is_device_ptr(out_indices) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
-            s = fail(ctx, FCP_ERR_CUDA, "indices copy failed");
+        FCP_TRY(crops.init(ctx, out_crops, (size_t)f * out_h * out_w * 3));
+        FCP_TRY(mats.init(ctx, out_matrices, sizeof(double) * 6 * f, true));
+        FCP_TRY(valid.init(ctx, out_valid, f, true));
+        FCP_TRY(align_core(ctx, ptr_table ? nullptr : dimg, n, h, w, ptr_table, hs_dev, ws_dev, pad.as<int32_t>(), face_img, nullptr,
+                           lms.as<float>(), f, tgt.as<float>(), out_w, out_h, border_mode, allow_skew, crops.as<uint8_t>(),
+                           mats.as<double>(), valid.as<uint8_t>()));
+        // ---- the one collective: this rank's face records, all-gathered on the side stream while the parser runs
+        if (ctx->gather_out)
+            FCP_TRY(gather_meta_async(ctx, lms.as<float>(), face_img, mats.as<double>(), valid.as<uint8_t>(), face_count,
+                                      ctx->gather_cap, ctx->gather_base, ctx->gather_out));
+        if (do_parse) {
+            FCP_TRY(lab.init(ctx, out_labels, (size_t)f * out_h * out_w));
+            FCP_TRY(hist.init(ctx, out_hist, sizeof(int32_t) * 19 * f));
+            FCP_TRY(parse_core(ctx, crops.as<uint8_t>(), f, out_h, out_w, lab.as<uint8_t>(), hist.as<int32_t>(), nullptr));
+        }
+        if (ctx->gather_out) FCP_TRY(gather_meta_join(ctx));
+        FCP_TRY(lms.flush(sizeof(float) * 10 * f));
+        FCP_TRY(crops.flush()); FCP_TRY(mats.flush()); FCP_TRY(valid.flush()); FCP_TRY(lab.flush()); FCP_TRY(hist.flush());
+        if (out_indices)
+            FCP_CUDA(ctx, cudaMemcpyAsync(out_indices, face_img, sizeof(int32_t) * f,
+                                          is_device_ptr(out_indices) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+    } else if (ctx->gather_out) {
+        FCP_TRY(gather_meta_async(ctx, lms.as<float>(), face_img, nullptr, nullptr, face_count, ctx->gather_cap, ctx->gather_base,
+                                  ctx->gather_out));
+        FCP_TRY(gather_meta_join(ctx));
     }
-    if (s == FCP_OK) {
-        if (is_device_ptr(out_count)) cudaMemcpyAsync(out_count, &count, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
-        else *out_count = count;
-        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) s = fail(ctx, FCP_ERR_CUDA, "sync failed");
-    }
-    cleanup();
-    if (s == FCP_OK && count > max_faces) return fail(ctx, FCP_ERR_CAPACITY, "max_faces too small: " + std::to_string(count) + " faces found");
-    return s;
+    if (is_device_ptr(out_count)) FCP_CUDA(ctx, cudaMemcpyAsync(out_count, &count, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    else *out_count = count;
+    FCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (count > max_faces) return fail(ctx, FCP_ERR_CAPACITY, "max_faces too small: " + std::to_string(count) + " faces found");
+    return FCP_OK;
 }
 
 int fcp_conv2d(fcp_ctx* ctx, const float* x, int n, int h, int w, int cin, const float* weight, int cout, int k, int stride,

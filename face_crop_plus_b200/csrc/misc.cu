@@ -147,7 +147,8 @@ __global__ void __launch_bounds__(256, 1) stem7_kernel(const void* __restrict__ 
 
 // ------------------------------------------------------------------------------- RRDB conv_first (3x3, Cin=3)
 // rrdb.py:77 conv_first on images/255 (rrdb.py:142); input f32 NCHW, output NHWC 64 channels, bias only.
-__global__ void __launch_bounds__(256) conv3_first_kernel(const float* __restrict__ src, float in_div, int N, int H,
+template <bool U8>
+__global__ void __launch_bounds__(256) conv3_first_kernel(const void* __restrict__ src_v, float in_div, int N, int H,
                                                           int W, const float* __restrict__ wkn,
                                                           const float* __restrict__ shift, float* __restrict__ out,
                                                           int out_cs, int out_co) {
@@ -170,7 +171,9 @@ __global__ void __launch_bounds__(256) conv3_first_kernel(const float* __restric
             if (hi < 0 || hi >= H || wi < 0 || wi >= W) continue;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                float x = __fdiv_rn(src[(((size_t)n * 3 + c) * H + hi) * W + wi], in_div);
+                const float raw = U8 ? (float)static_cast<const uint8_t*>(src_v)[(((size_t)n * H + hi) * W + wi) * 3 + c]
+                                     : static_cast<const float*>(src_v)[(((size_t)n * 3 + c) * H + hi) * W + wi];
+                float x = __fdiv_rn(raw, in_div);
                 const float* pw = sw + ((r * 3 + s) * 3 + c) * 64;
 #pragma unroll
                 for (int j = 0; j < 64; ++j) acc[j] = fmaf(x, pw[j], acc[j]);
@@ -358,8 +361,16 @@ int launch_stem_rows(fcp_ctx* ctx, const void* src, int mode, int n, int h, int 
 int launch_conv3_first(fcp_ctx* ctx, const float* src_nchw, float in_div, int n, int h, int w, const float* w_kn,
                        const float* shift, Tensor out) {
     size_t total = (size_t)n * h * w;
-    conv3_first_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(src_nchw, in_div, n, h, w, w_kn, shift,
-                                                                                 out.p, out.cs, out.co);
+    conv3_first_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(src_nchw, in_div, n, h, w, w_kn, shift,
+                                                                                        out.p, out.cs, out.co);
+    FCP_KERNEL_CHECK(ctx);
+    return FCP_OK;
+}
+
+int launch_conv3_first_u8(fcp_ctx* ctx, const uint8_t* src_nhwc, int n, int h, int w, const float* w_kn, const float* shift, Tensor out) {
+    size_t total = (size_t)n * h * w;
+    conv3_first_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(src_nhwc, 255.f, n, h, w, w_kn, shift,
+                                                                                       out.p, out.cs, out.co);
     FCP_KERNEL_CHECK(ctx);
     return FCP_OK;
 }

@@ -178,8 +178,9 @@ __global__ void multi_masks_kernel(const uint8_t* __restrict__ labels, size_t co
 }
 
 // x4: NHWC [n,4h,4w,cs] (3 valid channels) -> out NCHW [n,3,h,w] (image i at out + i*3*h*w)
+template <bool U8>
 __global__ void rrdb_tail_kernel(const float* __restrict__ x4, int cs, int co, int n, int h, int w,
-                                 float* __restrict__ out) {
+                                 void* __restrict__ out_v) {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t total = (size_t)n * h * w;
     if (idx >= total) return;
@@ -203,7 +204,8 @@ __global__ void rrdb_tail_kernel(const float* __restrict__ x4, int cs, int co, i
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         float v = fminf(fmaxf(acc[c], 0.f), 1.f);
-        out[(((size_t)im * 3 + c) * h + oy) * w + ox] = rintf(v * 255.f);
+        if (U8) static_cast<uint8_t*>(out_v)[(((size_t)im * h + oy) * w + ox) * 3 + c] = (uint8_t)rintf(v * 255.f);
+        else static_cast<float*>(out_v)[(((size_t)im * 3 + c) * h + oy) * w + ox] = rintf(v * 255.f);
     }
 }
 
@@ -255,7 +257,14 @@ int launch_multi_masks(fcp_ctx* ctx, const uint8_t* labels, size_t count, const 
 
 int launch_rrdb_tail(fcp_ctx* ctx, Tensor x4, float* out_nchw, int h, int w) {
     size_t total = (size_t)x4.n * h * w;
-    rrdb_tail_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(x4.p, x4.cs, x4.co, x4.n, h, w, out_nchw);
+    rrdb_tail_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(x4.p, x4.cs, x4.co, x4.n, h, w, out_nchw);
+    FCP_KERNEL_CHECK(ctx);
+    return FCP_OK;
+}
+
+int launch_rrdb_tail_u8(fcp_ctx* ctx, Tensor x4, uint8_t* out_nhwc, int h, int w) {
+    size_t total = (size_t)x4.n * h * w;
+    rrdb_tail_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(x4.p, x4.cs, x4.co, x4.n, h, w, out_nhwc);
     FCP_KERNEL_CHECK(ctx);
     return FCP_OK;
 }

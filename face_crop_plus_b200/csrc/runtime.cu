@@ -16,6 +16,23 @@ int fail(fcp_ctx* ctx, int code, const std::string& msg) {
     return code;
 }
 
+// ------------------------------------------------------------------------------------------------ stage timers
+StageScope::StageScope(fcp_ctx* c, int stage, cudaStream_t st, bool use_stream) : ctx(c), stream(use_stream ? st : c->stream) {
+    if (!ctx->profile) return;
+    if (ctx->stage_used == ctx->stage_recs.size()) {
+        fcp_ctx::StageRec r{};
+        if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+        ctx->stage_recs.push_back(r);
+    }
+    fcp_ctx::StageRec& r = ctx->stage_recs[ctx->stage_used++];
+    r.stage = stage;
+    cudaEventRecord(r.a, stream);
+    end = r.b;
+}
+StageScope::~StageScope() {
+    if (end) cudaEventRecord(end, stream);
+}
+
 // ------------------------------------------------------------------------------------------------------ Arena
 Arena::~Arena() {
     if (base_) cudaFree(base_);
@@ -360,6 +377,12 @@ void fcp_destroy(fcp_ctx* ctx) {
     for (void* p : ctx->device_allocs) cudaFree(p);
     for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->copy_events) cudaEventDestroy(e);
+    for (auto& r : ctx->stage_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    fcp_comm_destroy(ctx);
+    if (ctx->gather_send) cudaFree(ctx->gather_send);
+    if (ctx->comm_ready) cudaEventDestroy(ctx->comm_ready);
+    if (ctx->comm_done) cudaEventDestroy(ctx->comm_done);
+    if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -432,6 +455,27 @@ int fcp_profile_read(fcp_ctx* ctx, double* out4) {
     ctx->prof_recs.clear();
     out4[0] = ms; out4[1] = (double)(ctx->prof_used / 2); out4[2] = ctx->prof_flops; out4[3] = ctx->prof_bytes;
     ctx->prof_used = 0; ctx->prof_flops = 0; ctx->prof_bytes = 0;
+    return FCP_OK;
+}
+
+int fcp_profile_stages(fcp_ctx* ctx, double* out_ms8) {
+    if (!ctx || !out_ms8) return fail(ctx, FCP_ERR_INVALID, "fcp_profile_stages: bad argument");
+    FCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->comm_stream) FCP_CUDA(ctx, cudaStreamSynchronize(ctx->comm_stream));
+    for (int i = 0; i < 8; ++i) out_ms8[i] = 0.0;
+    for (size_t i = 0; i < ctx->stage_used; ++i) {
+        float t = 0;
+        const auto& r = ctx->stage_recs[i];
+        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess && r.stage >= 0 && r.stage < 8) out_ms8[r.stage] += t;
+        else cudaGetLastError();
+    }
+    ctx->stage_used = 0;
+    return FCP_OK;
+}
+
+int fcp_set_enhance(fcp_ctx* ctx, float min_face_factor) {
+    if (!ctx) return FCP_ERR_INVALID;
+    ctx->enh_threshold = min_face_factor;
     return FCP_OK;
 }
 

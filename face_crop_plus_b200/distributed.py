@@ -50,7 +50,14 @@ def gather_records(rec: torch.Tensor, capacity: int, group=None, device=None) ->
         dist.all_gather_into_tensor(out, buf, group=group)
     else:
         out = buf
-    out = out.cpu().view(world, capacity + 1, RECORD)
+    return unpack_records(out.cpu().view(world, capacity + 1, RECORD), capacity)
+
+
+def unpack_records(out, capacity: int) -> dict:
+    """[world, capacity + 1, RECORD] float64 blocks (torch tensor or numpy array; slot ``capacity`` = the rank's face count)
+    -> the batch-global metadata dict of :func:`gather_records`."""
+    out = torch.as_tensor(out).cpu()
+    world = out.shape[0]
     parts, owner = [], []
     for r in range(world):
         k = int(out[r, capacity, 0].item())
@@ -60,6 +67,17 @@ def gather_records(rec: torch.Tensor, capacity: int, group=None, device=None) ->
     return dict(landmarks=allrec[:, :10].to(torch.float32).view(-1, 5, 2).numpy(), indices=allrec[:, 10].long().tolist(),
                 matrices=allrec[:, 11:17].view(-1, 2, 3).numpy(), valid=allrec[:, 17].bool().numpy(),
                 owner=np.array(owner, dtype=np.int64))
+
+
+def init_comm(ctx, group=None) -> None:
+    """Creates the CUDA library's own NCCL communicator for ``ctx`` (one context per rank / GPU): rank 0 makes the NCCL
+    unique id, ``torch.distributed`` (any backend) carries its 128 bytes to the other ranks, then every rank joins.
+    After this, ``ctx.set_gather(buffer, cap, base)`` makes every ``ctx.pipeline`` call all-gather its face records on the
+    device, overlapped with the parser — no host round trip (``fcp_set_gather``)."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    ids = [ctx.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0, group=group)
+    ctx.comm_init(rank, world, ids[0])
 
 
 def process_sharded(run_local, images, rank: int, world: int, capacity_per_rank: int, group=None, device=None) -> dict:

@@ -37,6 +37,16 @@ def get_context(device) -> "_abi.Context":
         return _contexts[idx]
 
 
+def bind_stream(ctx: "_abi.Context") -> None:
+    """Runs the library on torch's CURRENT stream of the context's device, so that tensors produced by torch ops
+    (``.to(device)``, ``permute().contiguous()`` ...) are ordered before the kernels that read their ``data_ptr``.
+    Call it (under ``_lock``) before every C-ABI call that may receive a CUDA tensor."""
+    stream = torch.cuda.current_stream(ctx.device).cuda_stream
+    if getattr(ctx, "_bound_stream", None) != stream:
+        ctx.set_stream(stream)
+        ctx._bound_stream = stream
+
+
 class LoadMixin:
     """``LoadMixin`` of the reference (_layers.py:12-35): same cache location and URL, weights go to the CUDA library."""
     WEIGHTS_FILENAME: str | None = None
@@ -82,6 +92,7 @@ class RetinaFace(LoadMixin):
         if self.strategy not in _abi.STRATEGIES:
             raise ValueError(f"Unsupported startegy: {self.strategy}")          # retinaface.py:400 (sic)
         with _lock:
+            bind_stream(self.ctx)
             out = self.ctx.detect(images_u8_nhwc, self.vis_threshold, self.nms_threshold, self.strategy)
         return out["landmarks"], out["indices"].tolist()
 
@@ -113,17 +124,47 @@ class RRDBNet(LoadMixin):
             g[i] = (w * h / (height * width)).mean() <= self.min_face_factor
         return g
 
+    def predict_u8(self, images, landmarks=None, indices=None):
+        """Fast path of :meth:`predict` on uint8 NHWC data (an [N,H,W,3] array / CUDA tensor, or a list of [h,w,3] arrays):
+        the reference's result ``round(clamp(.)*255)`` is integral, so nothing is lost and no float32 NCHW copy is made.
+        Enhances the gated images in place and returns the container."""
+        is_list = isinstance(images, (list, tuple))
+        n = len(images)
+        if n == 0:
+            return images
+        h0, w0 = images[0].shape[:2]
+        if landmarks is None or indices is None:
+            g = np.ones(n, np.uint8)
+        else:
+            g = self.gate(n, h0, w0, np.asarray(landmarks, dtype=np.float32), list(indices))
+        if not g.any():
+            return images
+        with _lock:
+            bind_stream(self.ctx)
+            if not is_list:
+                self.ctx.enhance_u8(images, g)
+            else:
+                for i in np.nonzero(g)[0]:
+                    one = np.ascontiguousarray(images[i])[None]
+                    self.ctx.enhance_u8(one, None)
+                    images[i] = one[0]
+        return images
+
     @torch.no_grad()
     def predict(self, images, landmarks=None, indices=None):
         """``RRDBNet.predict`` (rrdb.py:83-146): enhances the gated images IN PLACE and returns the same container."""
         if isinstance(images, (list, tuple)):
             for i, img in enumerate(images):
-                sub_l = None if landmarks is None else landmarks[[idx == i for idx in indices]]
-                sub_i = None if indices is None else [0] * len(sub_l)
-                g = self.gate(1, *images[0].shape[1:], sub_l, sub_i)     # normalised by images[0] like the reference
-                if g[0]:
+                if landmarks is None or indices is None:
+                    enhance = True                                       # rrdb.py:125-127: no landmarks -> every image
+                else:
+                    sub_l = landmarks[[idx == i for idx in indices]]
+                    # normalised by images[0]'s size like the reference (rrdb.py:139)
+                    enhance = bool(self.gate(1, *images[0].shape[1:], sub_l, [0] * len(sub_l))[0])
+                if enhance:
                     batch = img.unsqueeze(0).contiguous()
                     with _lock:
+                        bind_stream(self.ctx)
                         self.ctx.enhance(batch, None)
                     images[i] = batch[0]
             return images
@@ -132,6 +173,7 @@ class RRDBNet(LoadMixin):
         if g.any():
             work = images if images.is_contiguous() else images.contiguous()
             with _lock:
+                bind_stream(self.ctx)
                 self.ctx.enhance(work.numpy() if (isinstance(work, torch.Tensor) and not work.is_cuda) else work, g)
             if work is not images:
                 images.copy_(work)
@@ -159,6 +201,7 @@ class BiSeNet(LoadMixin):
         if len(hist) == 0:
             return ({} if self.attr_groups is not None else None), ({} if self.mask_groups is not None else None)
         with _lock:
+            bind_stream(self.ctx)
             attr_m, mask_m, masks = self.ctx.group(np.ascontiguousarray(labels), np.ascontiguousarray(hist, dtype=np.int32),
                                                    self.attr_groups, self.mask_groups, self.attr_threshold, self.mask_threshold,
                                                    self.attr_join_by_and)
@@ -174,6 +217,7 @@ class BiSeNet(LoadMixin):
 
     def predict_u8(self, crops_u8_nhwc: np.ndarray):
         with _lock:
+            bind_stream(self.ctx)
             self.ctx.set_micro_batch(16, max(int(self.batch_size), 1))
             labels, hist = self.ctx.parse(np.ascontiguousarray(crops_u8_nhwc))
         return self.groups_from(labels, hist)

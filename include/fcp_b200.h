@@ -66,6 +66,10 @@ int fcp_set_conv_impl(fcp_ctx* ctx, int impl);
  * (2*M*Cout*K of the true, un-padded shapes), out[3] = algorithmic bytes (activations in+out, weights once per launch) */
 int fcp_profile(fcp_ctx* ctx, int enable);
 int fcp_profile_read(fcp_ctx* ctx, double* out4);
+/* while profiling is enabled every stage of the path is bracketed by an event pair as well; returns (and resets) the
+ * accumulated milliseconds: out[0] detector network, [1] decode + NMS + strategy, [2] enhance, [3] un-pad + solve + warp,
+ * [4] parser network, [5] parser tail (resize + argmax + histogram), [6] metadata all-gather (side stream), [7] ingest */
+int fcp_profile_stages(fcp_ctx* ctx, double* out_ms8);
 
 /* ---- weights: replaces LoadMixin.load / get_weights (models/_layers.py:16-35) ---------------------------
  * Feed every entry of the reference state_dict (same keys, float32, host memory, OIHW conv weights), then
@@ -150,6 +154,18 @@ int fcp_group(fcp_ctx* ctx, const uint8_t* labels, const int32_t* hist, int f, i
 int fcp_enhance(fcp_ctx* ctx, float* images, int n, int h, int w, const uint8_t* do_enhance);
 /* RRDBNet.forward: x f32 [n,3,h,w] in [0,1] -> out f32 [n,3,4h,4w] */
 int fcp_enhance_forward(fcp_ctx* ctx, const float* x, int n, int h, int w, float* out);
+/* the same predict() on a uint8 NHWC batch [n,h,w,3] (what Cropper holds before as_tensor, cropper.py:817): the
+ * reference's result round(clamp(bicubic(x4, 1/4), 0, 1) * 255) is integral, so uint8 in/out loses nothing and the
+ * float32 NCHW copies (12.6 MB per 1024x1024 image, each way) never exist.  In place where do_enhance[i] != 0. */
+int fcp_enhance_u8(fcp_ctx* ctx, uint8_t* images, int n, int h, int w, const uint8_t* do_enhance);
+/* the gate of RRDBNet.predict (rrdb.py:124-141) on the device: out_gate[i] = 1 iff image i has faces and the float32 mean
+ * of (x4-x0)*(y4-y0) / (h*w) over them is <= min_face_factor.  landmarks f32 [f,5,2], indices i32 [f] ascending. */
+int fcp_enhance_gate(fcp_ctx* ctx, const float* landmarks, const int32_t* indices, int f, int n, int h, int w,
+                     float min_face_factor, uint8_t* out_gate);
+/* min_face_factor >= 0 makes fcp_pipeline run the enhancement stage between detection and alignment (cropper.py:833-836:
+ * gate on the device from the un-padded landmarks, RRDBNet on the gated images of the uint8 batch, crops warped from the
+ * enhanced images); < 0 (default) turns it off.  Needs the RRDBNet weights. */
+int fcp_set_enhance(fcp_ctx* ctx, float min_face_factor);
 
 /* ---- whole path: the detect branch of Cropper.process_batch (cropper.py:815-847) in one call ------------
  * detect -> un-pad -> align -> parse with no host round trip between the stages.  Capacities as in fcp_detect;
@@ -160,6 +176,24 @@ int fcp_pipeline(fcp_ctx* ctx, const uint8_t* images, int n, int h, int w, const
                  int border_mode, int allow_skew, int max_faces, float* out_landmarks, int32_t* out_indices,
                  int32_t* out_count, uint8_t* out_crops, double* out_matrices, uint8_t* out_valid,
                  uint8_t* out_labels, int32_t* out_hist);
+
+/* ---- multi-GPU: batch sharding with ONE collective -----------------------------------------
+ * One process and one context per GPU; every rank runs the path on its shard of the images.  The only data that crosses
+ * devices is an all-gather of fixed-size per-face records over NCCL: 20 float64 per face = landmarks[10], GLOBAL image
+ * index, matrix[6], valid, 2 reserved; a rank's block is [cap + 1][20] with its face count in [cap][0].
+ * The reference has no multi-device code (one torch.device per Cropper, cropper.py:336-337).
+ * fcp_comm_unique_id: rank 0 creates the 128-byte NCCL id, the host side broadcasts it (any channel);
+ * fcp_comm_init: collective over all ranks.  NCCL is bound at run time (libnccl.so.2 of the process, or FCP_NCCL_LIB). */
+int fcp_comm_unique_id(fcp_ctx* ctx, void* out_id128);
+int fcp_comm_init(fcp_ctx* ctx, int rank, int world, const void* id128);
+void fcp_comm_destroy(fcp_ctx* ctx);
+/* explicit call: packs `count` local faces on the device and all-gathers; out_records f64 [world][cap + 1][20] */
+int fcp_allgather_meta(fcp_ctx* ctx, const float* landmarks, const int32_t* indices, const double* matrices,
+                       const uint8_t* valid, int count, int cap, int index_base, double* out_records);
+/* fused form: while out_records (DEVICE memory, [world][cap + 1][20]) is set, every fcp_pipeline call packs its face
+ * records right after the align stage and all-gathers them on a side stream, overlapped with the parser; the result is
+ * complete when fcp_pipeline returns.  index_base = global index of this rank's first image.  NULL turns it off. */
+int fcp_set_gather(fcp_ctx* ctx, double* out_records, int cap, int index_base);
 
 /* ---- kernel-level test hook: one fused convolution (what nn.Conv2d + BatchNorm2d + activation do in the
  * reference graphs).  x f32 NHWC [n,h,w,cin]; weight f32 OIHW host [cout,cin,k,k]; scale/shift f32 [cout] host

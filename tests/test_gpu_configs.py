@@ -1,0 +1,201 @@
+"""GPU parity at the sizes and paths of BASELINE.json's configurations that the stage tests do not reach:
+C4 (RRDBNet at 256x256, uint8 in/out, batched launches, 1024x1024 fit), full-size parsing (faces cropped from 1024x1024
+images), C5 (ingest -> detect -> enhance -> align -> parse with the enhancement stage INSIDE the one-call pipeline), the
+device-side enhancement gate, and the metadata records of the multi-GPU all-gather.  Everything goes through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+from face_crop_plus_b200 import synth
+from face_crop_plus_b200.landmarks import landmarks_target
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+TOL = 1e-3                # float32 tolerance stated by north_star
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from face_crop_plus_b200 import _abi
+    c = _abi.Context(0)
+    c.load_state_dict(_abi.MODEL_RETINAFACE, synth.make_state_dict("retinaface", 0, class_bias=4.0))
+    c.load_state_dict(_abi.MODEL_BISENET, synth.make_state_dict("bisenet", 0))
+    c.load_state_dict(_abi.MODEL_RRDBNET, synth.make_state_dict("rrdbnet", 0))
+    yield c
+    c.close()
+
+
+# ------------------------------------------------------------------------------------------------- C4: RRDBNet
+def test_enhance_forward_256_vs_oracle(ctx):
+    """BASELINE.json configs[3] size: RRDBNet.forward on a 256x256 image (351 convs, 1024x1024 output) against the oracle."""
+    from oracle import nets
+    sd = synth.make_state_dict("rrdbnet", 0)
+    x = torch.from_numpy(synth.make_images(1, 256, 256, seed=31)).permute(0, 3, 1, 2).float().contiguous() / 255
+    ref = nets.rrdbnet_forward(x, sd).numpy()
+    got = ctx.enhance_forward(x.numpy())
+    err = float(np.abs(got - ref).max())
+    print(f"RRDBNet.forward 256x256: max-abs err {err:.3e} (|ref| max {np.abs(ref).max():.3f})")
+    assert got.shape == (1, 3, 1024, 1024) and err < TOL
+
+
+def test_enhance_u8_batched_equals_per_image_and_f32_path(ctx):
+    """uint8 NHWC predict (the pipeline's form) == the float32 NCHW predict of rrdb.py:142-144, image by image, and the
+    batched launches (5 gated images of 7 share launches) change nothing: images are independent."""
+    imgs = synth.make_images(7, 48, 40, seed=77)
+    gate = np.array([1, 0, 1, 1, 0, 1, 1], np.uint8)
+    a = imgs.copy()
+    ctx.enhance_u8(a, gate)
+    assert np.array_equal(a[gate == 0], imgs[gate == 0]) and not np.array_equal(a[0], imgs[0])
+    dev = torch.from_numpy(imgs).cuda()
+    ctx.enhance_u8(dev, gate)
+    assert np.array_equal(dev.cpu().numpy(), a)
+    for i in np.nonzero(gate)[0]:
+        one = imgs[i:i + 1].copy()
+        ctx.enhance_u8(one, None)                                        # a batch of one
+        f32 = torch.from_numpy(imgs[i:i + 1]).permute(0, 3, 1, 2).float().contiguous().numpy()
+        ctx.enhance(f32, None)
+        assert np.array_equal(one[0], a[i])
+        assert np.array_equal(f32[0].transpose(1, 2, 0).astype(np.uint8), a[i])
+
+
+def test_enhance_1024_fits_and_centre_window_vs_oracle(ctx):
+    """What C5 feeds the enhancer: one 1024x1024 image (4096x4096 intermediates, ~13 GB of arena).  The oracle cannot run
+    that size in test time, so a 160x160 window is enhanced by the oracle on its own and compared away from its borders
+    (the receptive field decays geometrically with depth thanks to the x0.2 residual scaling; 48 px of margin)."""
+    from oracle import enhance as oenh
+    img = synth.make_images(1, 1024, 1024, seed=5)
+    out = img.copy()
+    ctx.enhance_u8(out, None)
+    assert out.shape == img.shape and not np.array_equal(out, img)
+    y0, x0, s, m = 400, 512, 160, 48
+    win = torch.from_numpy(img[0, y0:y0 + s, x0:x0 + s]).permute(2, 0, 1).float()
+    ref = oenh.enhance_image(win, synth.make_state_dict("rrdbnet", 0)).permute(1, 2, 0).numpy()
+    d = np.abs(out[0, y0 + m:y0 + s - m, x0 + m:x0 + s - m].astype(int) - ref[m:-m, m:-m].astype(int))
+    print(f"1024x1024 enhance, centre window vs oracle: max |diff| {d.max()}, mismatching bytes {(d > 0).mean():.3%}")
+    assert d.max() <= 2 and (d > 0).mean() < 0.35
+
+
+def test_enhance_gate_device_equals_host(ctx):
+    """rrdb.py:124-141 on the device vs the numpy gate of the host mirror, including images with >= 8 and > 128 faces
+    (numpy's pairwise float32 summation) and images without faces."""
+    from face_crop_plus_b200.models import RRDBNet
+    rng = np.random.default_rng(3)
+    counts = [0, 1, 3, 0, 8, 9, 17, 130, 300, 2, 0]
+    indices = np.repeat(np.arange(len(counts)), counts).astype(np.int32)
+    lms = (rng.random((len(indices), 5, 2)) * 1024).astype(np.float32)
+    lms[:, 4] = lms[:, 0] + (rng.random((len(indices), 2)) * 60 + 1).astype(np.float32)
+    host = RRDBNet.__new__(RRDBNet)
+    for thr in (0.0005, 0.001, 0.002, 0.0008765):
+        host.min_face_factor = thr
+        ref = host.gate(len(counts), 1024, 1024, lms, indices.tolist())
+        got = ctx.enhance_gate(lms, indices, len(counts), 1024, 1024, thr)
+        assert np.array_equal(got, ref), (thr, got, ref)
+    # knife edge: thresholds equal to the float32 means themselves
+    for i in (1, 4, 7, 8):
+        sel = lms[indices == i]
+        w, h = (sel[:, 4] - sel[:, 0]).T
+        thr = float((w * h / (1024 * 1024)).mean())
+        host.min_face_factor = thr
+        assert np.array_equal(ctx.enhance_gate(lms, indices, len(counts), 1024, 1024, thr),
+                              host.gate(len(counts), 1024, 1024, lms, indices.tolist()))
+
+
+# --------------------------------------------------------------------------------------------- full-size parsing
+def test_parse_faces_from_1024_images_vs_oracle(ctx):
+    """BiSeNet.predict on 8 faces produced by the real path at the bench size (crops warped out of 1024x1024 images by the
+    detector's own landmarks) against oracle.parse: logits within the float tolerance, labels equal except at near-ties of
+    the oracle's own logits."""
+    from oracle import nets, parse as oparse
+    imgs = synth.make_images(8, 1024, 1024, seed=1234)
+    out = ctx.pipeline(imgs, None, landmarks_target((256, 256), 0.65), (256, 256), 0.6, 0.4, "largest")
+    crops = out["crops"]
+    assert len(crops) == 8
+    sd = synth.make_state_dict("bisenet", 0)
+    ref_logits = nets.bisenet_logits64(oparse.preprocess(crops), sd)
+    got_logits = ctx.parse_logits(crops)
+    err = float(np.abs(got_logits - ref_logits.numpy()).max())
+    ref_labels = oparse.labels_from_logits64(ref_logits, (512, 512), (256, 256))
+    labels, hist = ctx.parse(crops)
+    diff = labels != ref_labels
+    print(f"parse of 8 faces from 1024x1024 images: logits max-abs err {err:.3e}, label mismatch {diff.mean():.3e}")
+    assert err < TOL
+    assert np.array_equal(labels, out["labels"]) and np.array_equal(hist, out["hist"])      # pipeline == stage call
+    if diff.any():
+        up = torch.nn.functional.interpolate(torch.nn.functional.interpolate(ref_logits, (512, 512), None, "bilinear", True),
+                                             (256, 256), mode="nearest")
+        top2 = up.topk(2, dim=1).values
+        margin = (top2[:, 0] - top2[:, 1]).numpy()
+        assert margin[diff].max() < 2 * TOL and diff.mean() < 1e-3
+
+
+# ------------------------------------------------------------------------------- C5: the full pipeline, one call
+def test_full_pipeline_mixed_resolution_with_enhancement_vs_oracle(ctx):
+    """BASELINE.json configs[4] at oracle-feasible sizes: 6 images of mixed resolution -> as_batch (256x256, centred padding) ->
+    detect -> enhancement of the gated images (threshold picked so that 2 of them are gated on) -> align -> parse, the
+    enhancement stage running INSIDE fcp_pipeline on the device, against oracle.pipeline.process_batch(enh_sd=...)."""
+    from oracle import ingest as oingest, pipeline as opipe
+    sizes = [(141, 250), (300, 200), (256, 256), (620, 410), (97, 180), (512, 384)]
+    images = [synth.make_images(1, h, w, seed=900 + i)[0] for i, (h, w) in enumerate(sizes)]
+    det_sd = synth.make_state_dict("retinaface", 0, class_bias=4.0)
+    par_sd = synth.make_state_dict("bisenet", 0)
+    enh_sd = synth.make_state_dict("rrdbnet", 0)
+    ref_batch, _, ref_pads = oingest.as_batch(images, 256)
+    batch, _, pads = ctx.as_batch(images, 256)
+    assert np.array_equal(pads, ref_pads)
+    if not np.array_equal(batch, ref_batch):              # INTER_CUBIC images: OpenCV's own arithmetic, see tests/test_gpu_ingest.py
+        assert np.abs(batch.astype(int) - ref_batch.astype(int)).max() <= 1
+        batch = ref_batch
+    lms, idx, _, _ = opipe.detect(ref_batch, det_sd, 0.6, 0.4, "largest")
+    lms = lms - np.asarray(ref_pads)[idx][:, None, [2, 0]]
+    factors = np.array([(l[4, 0] - l[0, 0]) * (l[4, 1] - l[0, 1]) / np.float32(256 * 256) for l in lms], np.float32)
+    fs = np.sort(factors)
+    thr = float((fs[1] + fs[2]) / 2)                       # the two smallest faces are enhanced (threshold away from both)
+    ref = opipe.process_batch(ref_batch, det_sd, par_sd, enh_sd, paddings=ref_pads, strategy="largest", enh_threshold=thr)
+    tgt = landmarks_target((256, 256), 0.65)
+    ctx.set_enhance(thr)
+    try:
+        out = ctx.pipeline(np.ascontiguousarray(batch), pads, tgt, (256, 256), 0.6, 0.4, "largest")
+    finally:
+        ctx.set_enhance(None)
+    plain = ctx.pipeline(np.ascontiguousarray(batch), pads, tgt, (256, 256), 0.6, 0.4, "largest")
+    assert out["indices"].tolist() == ref["indices"]
+    assert np.abs(out["landmarks"] - ref["landmarks"]).max() < TOL
+    gated = [i for i, f in zip(ref["indices"], factors) if f <= np.float32(thr)]
+    assert len(gated) == 2
+    d = np.abs(out["crops"].astype(int) - ref["crops"].astype(int))
+    changed = [k for k in range(len(out["crops"])) if not np.array_equal(out["crops"][k], plain["crops"][k])]
+    assert sorted(out["indices"][changed].tolist()) == sorted(gated)          # exactly the gated images were rebuilt
+    lab = (out["labels"] != ref["labels"]).mean()
+    print(f"C5 (enhance inside the pipeline) vs oracle: crop px mismatch {(d > 0).mean():.3e} (max {d.max()}), label mismatch {lab:.3e}")
+    assert (d > 0).mean() < 0.02 and d.max() <= 16 and lab < 5e-3
+
+
+# ------------------------------------------------------------------------------------ multi-GPU metadata records
+def test_allgather_meta_single_rank_roundtrip(ctx):
+    """The device-side record packing of the one collective (world size 1: no NCCL traffic): pack -> unpack is the identity
+    and matches the Python packer of the gloo path bit for bit."""
+    from face_crop_plus_b200 import distributed as D
+    rng = np.random.default_rng(0)
+    f, cap = 11, 16
+    lms = rng.random((f, 5, 2)).astype(np.float32) * 1000
+    idx = np.sort(rng.integers(0, 8, f)).astype(np.int32)
+    mats = rng.standard_normal((f, 2, 3))
+    valid = (rng.random(f) > 0.2).astype(np.uint8)
+    rec = ctx.allgather_meta(lms, idx, mats, valid, cap, index_base=256)
+    assert rec.shape == (1, cap + 1, 20) and rec[0, cap, 0] == f
+    ref = D.pack_records(lms, idx, mats, valid, 256).numpy()
+    assert np.array_equal(rec[0, :f], ref) and not rec[0, f:cap].any()
+    got = D.unpack_records(rec, cap)
+    assert got["indices"] == (idx + 256).tolist() and np.array_equal(got["landmarks"], lms)
+    assert np.array_equal(got["matrices"], mats) and np.array_equal(got["valid"], valid.astype(bool))
+    # fused form: fcp_pipeline fills the records itself (side stream, overlapped with the parser)
+    imgs = synth.make_images(3, 256, 320, seed=2000)
+    buf = torch.zeros((1, 4 + 1, 20), dtype=torch.float64, device="cuda")
+    ctx.set_gather(buf, 4, 100)
+    try:
+        out = ctx.pipeline(imgs, None, landmarks_target((256, 256), 0.65), (256, 256), 0.6, 0.4, "largest")
+    finally:
+        ctx.set_gather(None)
+    got = D.unpack_records(buf, 4)
+    assert got["indices"] == (out["indices"] + 100).tolist() and np.array_equal(got["landmarks"], out["landmarks"])
+    assert np.array_equal(got["matrices"], out["matrices"]) and np.array_equal(got["valid"], out["valid"].astype(bool))

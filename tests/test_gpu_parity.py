@@ -334,8 +334,11 @@ def test_pipeline_matches_oracle(det_ctx, par_ctx):
         # crops: identical wherever the fixed-point source coordinates agree; landmark noise of ~1e-4 px can move a
         # 1/32-px interpolation bin, so compare pixel values with a small tolerance and require near-total equality
         d = np.abs(out["crops"].astype(int) - ref["crops"].astype(int))
+        lab = (out["labels"] != ref["labels"]).mean()
+        print(f"pipeline vs oracle ({strategy}): landmarks {np.abs(out['landmarks'] - ref['landmarks']).max():.2e} px, crop px mismatch "
+              f"{(d > 0).mean():.3e} (max {d.max()}), label mismatch {lab:.3e}")
         assert (d > 0).mean() < 0.02 and d.max() <= 16
-        assert (out["labels"] != ref["labels"]).mean() < 5e-3
+        assert lab < 5e-3
 
 
 def test_enhance_forward_64x64_and_linearity_property(enh_ctx):

@@ -42,3 +42,41 @@ def test_parse_landmarks_file(tmp_path):
     p.write_text("a.jpg 1 2 3 4 5 6 7 8 9 10\nb.jpg 10 9 8 7 6 5 4 3 2 1\n")
     lms, names = utils.parse_landmarks_file(str(p))
     assert lms.shape == (2, 5, 2) and names.tolist() == ["a.jpg", "b.jpg"] and lms[1, 0].tolist() == [10, 9]
+
+
+def test_rrdb_predict_list_without_landmarks_enhances_everything(monkeypatch):
+    """rrdb.py:125-127: landmarks None (enhance-only mode of Cropper) -> every image of a list is enhanced."""
+    import torch
+    from face_crop_plus_b200 import models
+
+    class FakeCtx:
+        device = 0
+        calls = 0
+
+        def enhance(self, batch, gate):
+            self.calls += 1
+            batch += 1
+            return batch
+
+    monkeypatch.setattr(models, "bind_stream", lambda ctx: None)
+    m = models.RRDBNet(0.001)
+    m.ctx = FakeCtx()
+    imgs = [torch.zeros((3, 4, 5)), torch.zeros((3, 6, 2))]
+    out = m.predict(imgs, None, [0, 1])
+    assert m.ctx.calls == 2 and all(float(o.min()) == 1.0 for o in out)
+    out = m.predict([torch.zeros((3, 4, 5))], None, None)
+    assert m.ctx.calls == 3
+    # with landmarks: image 1 has no faces -> skipped; image 0 gated by its face factor (normalised by images[0])
+    lms = np.zeros((1, 5, 2), np.float32)
+    lms[0, 4] = [1.0, 1.0]
+    m.ctx.calls = 0
+    m.predict([torch.zeros((3, 100, 100)), torch.zeros((3, 50, 50))], lms, [0])
+    assert m.ctx.calls == 1
+
+
+def test_parse_landmarks_csv_skips_header(tmp_path):
+    """utils.py:70-71: a .csv is read with delimiter ',' and its header row skipped."""
+    p = tmp_path / "l.csv"
+    p.write_text("name,x1,y1,x2,y2,x3,y3,x4,y4,x5,y5\na.jpg,1,2,3,4,5,6,7,8,9,10\nb.jpg,10,9,8,7,6,5,4,3,2,1\n")
+    lms, names = utils.parse_landmarks_file(str(p))
+    assert lms.shape == (2, 5, 2) and names.tolist() == ["a.jpg", "b.jpg"] and lms[0, 4].tolist() == [9, 10]
