@@ -56,7 +56,7 @@ SIGNATURES = {
     "fcp_enhance_forward": (_i, [_p, _p, _i, _i, _i, _p]),
     "fcp_enhance_u8": (_i, [_p, _p, _i, _i, _i, _p]),
     "fcp_enhance_gate": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _p]),
-    "fcp_set_enhance": (_i, [_p, _f]),
+    "fcp_set_enhance": (_i, [_p, _i, _f]),
     "fcp_comm_unique_id": (_i, [_p, _p]),
     "fcp_comm_init": (_i, [_p, _i, _i, _p]),
     "fcp_comm_destroy": (None, [_p]),
@@ -380,7 +380,7 @@ class Context:
 
     def set_enhance(self, min_face_factor: float | None):
         """Enhancement stage of :meth:`pipeline`: the ``min_face_factor`` of ``RRDBNet`` or None = off."""
-        self.check(self.lib.fcp_set_enhance(self.h, -1.0 if min_face_factor is None else float(min_face_factor)))
+        self.check(self.lib.fcp_set_enhance(self.h, int(min_face_factor is not None), float(min_face_factor or 0.0)))
 
     def enhance_forward(self, x_nchw):
         x = np.ascontiguousarray(x_nchw, dtype=np.float32)

@@ -130,8 +130,10 @@ struct fcp_ctx {
     struct StageRec { int stage; cudaEvent_t a, b; };
     std::vector<StageRec> stage_recs;
     size_t stage_used = 0;
-    // RRDBNet stage of fcp_pipeline (fcp_set_enhance): < 0 = off, else the min_face_factor threshold of rrdb.py:141
-    float enh_threshold = -1.f;
+    // RRDBNet stage of fcp_pipeline (fcp_set_enhance): on/off + the min_face_factor threshold of rrdb.py:141 (any float: the
+    // face factor of a mirrored / degenerate landmark set is negative)
+    bool enh_enabled = false;
+    float enh_threshold = 0.001f;
     // multi-GPU metadata all-gather (comm.cu): NCCL communicator + side stream; gather_out != nullptr makes fcp_pipeline
     // pack and all-gather its face records on comm_stream while the parser runs
     void* nccl_comm = nullptr;

@@ -982,7 +982,7 @@ int fcp_pipeline(fcp_ctx* ctx, const uint8_t* images, int n, int h, int w, const
                  uint8_t* out_crops, double* out_matrices, uint8_t* out_valid, uint8_t* out_labels, int32_t* out_hist) {
     FCP_TRY(need_model(ctx, FCP_MODEL_RETINAFACE));
     const bool do_parse = out_labels || out_hist;
-    const bool do_enhance = ctx->enh_threshold >= 0.f;
+    const bool do_enhance = ctx->enh_enabled;
     if (do_parse) FCP_TRY(need_model(ctx, FCP_MODEL_BISENET));
     if (do_enhance) FCP_TRY(need_model(ctx, FCP_MODEL_RRDBNET));
     if (!images || n < 1 || max_faces < 1 || !out_count || !target || !out_crops || strategy < 0 || strategy > 2 ||

@@ -473,8 +473,9 @@ int fcp_profile_stages(fcp_ctx* ctx, double* out_ms8) {
     return FCP_OK;
 }
 
-int fcp_set_enhance(fcp_ctx* ctx, float min_face_factor) {
+int fcp_set_enhance(fcp_ctx* ctx, int enable, float min_face_factor) {
     if (!ctx) return FCP_ERR_INVALID;
+    ctx->enh_enabled = enable != 0;
     ctx->enh_threshold = min_face_factor;
     return FCP_OK;
 }

@@ -162,10 +162,10 @@ int fcp_enhance_u8(fcp_ctx* ctx, uint8_t* images, int n, int h, int w, const uin
  * of (x4-x0)*(y4-y0) / (h*w) over them is <= min_face_factor.  landmarks f32 [f,5,2], indices i32 [f] ascending. */
 int fcp_enhance_gate(fcp_ctx* ctx, const float* landmarks, const int32_t* indices, int f, int n, int h, int w,
                      float min_face_factor, uint8_t* out_gate);
-/* min_face_factor >= 0 makes fcp_pipeline run the enhancement stage between detection and alignment (cropper.py:833-836:
- * gate on the device from the un-padded landmarks, RRDBNet on the gated images of the uint8 batch, crops warped from the
- * enhanced images); < 0 (default) turns it off.  Needs the RRDBNet weights. */
-int fcp_set_enhance(fcp_ctx* ctx, float min_face_factor);
+/* enable != 0 makes fcp_pipeline run the enhancement stage between detection and alignment (cropper.py:833-836: gate on
+ * the device from the un-padded landmarks, RRDBNet on the gated images of the uint8 batch, crops warped from the enhanced
+ * images); off by default.  Needs the RRDBNet weights. */
+int fcp_set_enhance(fcp_ctx* ctx, int enable, float min_face_factor);
 
 /* ---- whole path: the detect branch of Cropper.process_batch (cropper.py:815-847) in one call ------------
  * detect -> un-pad -> align -> parse with no host round trip between the stages.  Capacities as in fcp_detect;
