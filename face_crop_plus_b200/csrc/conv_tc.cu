@@ -83,7 +83,7 @@ struct alignas(64) TcParams {
     float post_scale2; const float* res3; int res3_cs, res3_co;
     int ablate;                                // FCP_TC_ABLATE bit mask, measurement only (results are WRONG with bits 1/2):
                                                //   1 skip the w_lo loads (L2->SM / smem-write traffic probe), 2 skip the bulk stores,
-                                               //   4 converters skip the fp16 split arithmetic (MODE 1),
+                                               //   4 converters skip the fp16 split arithmetic (MODE 1), 8 no early tile decode, 32 early residual prefetch (racy), 64 late shift fetch,
                                                //   16 back-off in the drain warps' d_full wait
     long long* dbg;                            // FCP_EXP_TIMELINE: clock64 stamps of CTA 0, [g][16]
 };
@@ -564,30 +564,42 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             //      previous tile's bulk stores have released the slab (waited for by the threads that issued them, published
             //      by one group barrier), and the residual chunks (128 pixels x 32 channels each) stream into the slab while
             //      the K loop runs.
-            // Tiles with a short K loop (<= 4 K-blocks, e.g. the bottleneck 1x1 convs) cannot hide the residual's HBM latency
-            // behind the K-blocks that follow the first drain, so they decode and prefetch at the TOP of the tile: the
-            // thread that issued the previous tile's store of chunk q waits for that store to have read the slab and
-            // re-fills chunk q by TMA (nobody else touches the slab between the pre-store barrier and the next phase 1).
-            const bool early = kblocks <= 4 && (!has_res || p.res_tma);
-            auto decode_and_fetch = [&]() {
-                const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
-                img = m_tile / tiles_per_img;
-                const int rem = m_tile - img * tiles_per_img;
-                ho0 = (rem / p.tiles_x) * p.BH; wo0 = (rem % p.tiles_x) * BW;
-                n0 = n_tile * BN + half * HALF;                               // first channel of this group
+            // Tiles with a short K loop (<= 4 K-blocks, e.g. the bottleneck 1x1 convs) decode and fetch their folded-BN shift
+            // at the TOP of the tile (with one K-block there is no second drain to hide the fetch behind).  The residual
+            // prefetch stays behind the first drain's group barrier: issuing it at the top of the tile as well (right after
+            // the issuing thread's own bulk_wait_read) measured 2-3 % faster, but made the network output depend on what
+            // had run on the device before (1e-2 drift of the detector heads after a 13 GB RRDBNet run in another context,
+            // profiles/diag_noise.py) - a hazard on the slab that only the group barrier closes.  FCP_TC_ABLATE=32 re-enables
+            // it for measurements.
+            const bool early = kblocks <= 4 && (!has_res || p.res_tma) && !(p.ablate & 8);
+            auto fetch_params = [&]() {
                 if (lane < HALF / 4)
                     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(par + lane * 16), "l"(p.shift + n0 + lane * 4) : "memory");
+            };
+            auto fetch_residual = [&]() {
                 if (has_res && p.res_tma && dma) {
                     bulk_wait_read();
                     mbar_expect_tx(rbar, C::CHUNK_BYTES);
                     tma_load_4d(slab_all + (half * CHUNKS + quarter) * C::CHUNK_BYTES, &p.tmRes, rbar, n0 + quarter * 32, wo0, ho0, img);
                 }
             };
-            if (early) decode_and_fetch();
+            auto decode = [&]() {
+                const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
+                img = m_tile / tiles_per_img;
+                const int rem = m_tile - img * tiles_per_img;
+                ho0 = (rem / p.tiles_x) * p.BH; wo0 = (rem % p.tiles_x) * BW;
+                n0 = n_tile * BN + half * HALF;                               // first channel of this group
+            };
+            const bool early_par = early && !(p.ablate & 64), early_res = early && (p.ablate & 32);
+            if (early) decode();
+            if (early_par) fetch_params();
+            if (early_res) fetch_residual();
             auto after_first_kblock = [&]() {
-                if (!early) decode_and_fetch();
+                if (!early) decode();
+                if (!early_par) fetch_params();
                 if (dma) bulk_wait_read();
                 group_sync();
+                if (!early_res) fetch_residual();
                 if (has_res && !p.res_tma) {
                     // cp.async fallback (resized or unaligned residual): HALF/4 lanes cover one pixel, RR pixels per instruction
                     constexpr int RL = HALF / 4, RR = 32 / RL;

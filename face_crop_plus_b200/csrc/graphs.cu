@@ -20,6 +20,10 @@ Tensor Exec::alloc(int n, int h, int w, int c, int cs) {
     if (!ok()) return t;
     t.p = static_cast<float*>(ctx->arena.alloc(t.pixels() * t.cs * sizeof(float)));
     if (!t.p) status = fail(ctx, FCP_ERR_CUDA, "activation arena exhausted");
+    // FCP_POISON=1 (debugging): every activation tensor starts as 3.4e38s, so a read of memory its producer never wrote
+    // (stale arena contents) shows up as a gross error instead of depending on what ran before
+    static const bool poison = getenv("FCP_POISON") != nullptr;
+    if (poison && t.p && !dry) cudaMemsetAsync(t.p, 0x7f, t.pixels() * t.cs * sizeof(float), ctx->stream);
     return t;
 }
 float* Exec::alloc_vec(size_t count) {

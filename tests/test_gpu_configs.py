@@ -72,7 +72,7 @@ def test_enhance_1024_fits_and_centre_window_vs_oracle(ctx):
     ref = oenh.enhance_image(win, synth.make_state_dict("rrdbnet", 0)).permute(1, 2, 0).numpy()
     d = np.abs(out[0, y0 + m:y0 + s - m, x0 + m:x0 + s - m].astype(int) - ref[m:-m, m:-m].astype(int))
     print(f"1024x1024 enhance, centre window vs oracle: max |diff| {d.max()}, mismatching bytes {(d > 0).mean():.3%}")
-    assert d.max() <= 2 and (d > 0).mean() < 0.35
+    assert d.max() <= 1 and (d > 0).mean() < 0.01          # observed: identical bytes
 
 
 def test_enhance_gate_device_equals_host(ctx):
@@ -167,7 +167,7 @@ def test_full_pipeline_mixed_resolution_with_enhancement_vs_oracle(ctx):
     assert sorted(out["indices"][changed].tolist()) == sorted(gated)          # exactly the gated images were rebuilt
     lab = (out["labels"] != ref["labels"]).mean()
     print(f"C5 (enhance inside the pipeline) vs oracle: crop px mismatch {(d > 0).mean():.3e} (max {d.max()}), label mismatch {lab:.3e}")
-    assert (d > 0).mean() < 0.02 and d.max() <= 16 and lab < 5e-3
+    assert (d > 0).mean() < 1.5e-3 and d.max() <= 16 and lab < 2e-4      # observed 4.2e-4 (max 7) / 6.4e-5
 
 
 # ------------------------------------------------------------------------------------ multi-GPU metadata records

@@ -337,8 +337,9 @@ def test_pipeline_matches_oracle(det_ctx, par_ctx):
         lab = (out["labels"] != ref["labels"]).mean()
         print(f"pipeline vs oracle ({strategy}): landmarks {np.abs(out['landmarks'] - ref['landmarks']).max():.2e} px, crop px mismatch "
               f"{(d > 0).mean():.3e} (max {d.max()}), label mismatch {lab:.3e}")
-        assert (d > 0).mean() < 0.02 and d.max() <= 16
-        assert lab < 5e-3
+        # observed on B200 (round 2): 1.3e-3 .. 1.4e-3 of the crop bytes differ (max 8), 1.0e-4 of the labels; bounds = ~2x observed
+        assert (d > 0).mean() < 3e-3 and d.max() <= 16
+        assert lab < 3e-4
 
 
 def test_enhance_forward_64x64_and_linearity_property(enh_ctx):
@@ -377,6 +378,14 @@ def test_detect_full_size_vs_oracle(ctx):
         # within an image faces are ordered by score; 200+ random faces contain scores that differ by < 1e-6 (float32
         # spacing near 1.0 is 6e-8), so the order may differ only between such near-ties
         pos = {k: j for j, k in enumerate(got)}
+        worst = max(float(np.abs(out["landmarks"][pos[k]] - lms[j]).max()) for j, k in enumerate(ref))
+        ctx.set_conv_impl(0)                               # second witness: the CUDA-core fp32 kernel on the same device
+        w0 = ctx.detect(imgs, 0.6, 0.4, strategy)
+        ctx.set_conv_impl(2)
+        p0 = {k: j for j, k in enumerate(zip(w0["indices"].tolist(), w0["anchors"].tolist()))}
+        worst0 = max(float(np.abs(w0["landmarks"][p0[k]] - lms[j]).max()) for j, k in enumerate(ref) if k in p0)
+        print(f"detect 1024x1024 ({strategy}): {len(ref)} faces, max landmark err vs oracle: tensor-core {worst:.3e} px, "
+              f"cuda-core fp32 {worst0:.3e} px (torch CPU threads {torch.get_num_threads()})")
         for j, k in enumerate(ref):
             if pos[k] != j:
                 assert abs(float(out["scores"][pos[k]]) - float(out["scores"][j])) < 1e-5
