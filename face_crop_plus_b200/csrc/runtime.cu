@@ -315,6 +315,13 @@ DevOut::~DevOut() {
 int run_conv(fcp_ctx* ctx, const ConvOp& op) {
     const bool tc = op.impl >= 1 && conv_tc_supported(op);   // shapes the tensor-core kernel does not cover use the CUDA-core kernel
     if (!tc && !op.wt->w_kn) return fail(ctx, FCP_ERR_INVALID, "conv: this packing exists for the tensor-core kernel only");
+    static const bool log_conv = getenv("FCP_LOG_CONV") != nullptr;      // one line per tensor-core launch, in launch order:
+    if (log_conv && tc) {                                                  // lets an ncu capture (-k conv_tc -s N) be matched to layer shapes
+        static long long seq = 0;
+        const ConvWeights& w = *op.wt;
+        fprintf(stderr, "[conv_tc %lld] impl=%d k=%dx%d s=%d cin=%d cout=%d M=%zu res=%d\n", seq++, op.impl, w.kh ? w.kh : w.k, w.kw ? w.kw : w.k,
+                op.stride, w.cin, w.cout, op.out.pixels(), (int)(op.res1 || op.res2));
+    }
     if (!ctx->profile) return tc ? launch_conv_tc(ctx, op) : launch_conv_ffma(ctx, op);
     if (ctx->prof_used + 2 > ctx->prof_events.size()) {
         cudaEvent_t a, b;
