@@ -284,8 +284,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     uint64_t* d_full = a_free + C::LANDINGS;       // [ISSUERS]  partial sum of one K-block is complete in TMEM buffer b
     uint64_t* d_empty = d_full + C::ISSUERS;       // [ISSUERS]  buffer b has been drained to registers
     uint64_t* res_bar = d_empty + C::ISSUERS;      // [2]  (first GROUPS used) residual chunks of the group's tile have landed
-    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(res_bar + 2);
-    static_assert((3 * C::STAGES + 2 * C::LANDINGS + 2 * C::ISSUERS + 2) * 8 + 4 <= 512, "barrier area");
+    uint64_t* par_bar = res_bar + 2;               // [2]  (first GROUPS used) folded-BN shift of the group's tile has landed
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(par_bar + 2);
+    static_assert((3 * C::STAGES + 2 * C::LANDINGS + 2 * C::ISSUERS + 4) * 8 + 4 <= 512, "barrier area");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto stage_b_hi = [&](int s) { return smem + s * C::B_SLOT_BYTES; };
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_b[s], 1); mbar_init(&conv[s], 4); mbar_init(&empty[s], 1); }
         for (int l = 0; l < C::LANDINGS; ++l) { mbar_init(&full_a[l], 1); mbar_init(&a_free[l], 4); }
         for (int a = 0; a < C::ISSUERS; ++a) { mbar_init(&d_full[a], 1); mbar_init(&d_empty[a], C::EPI_WARPS); }
-        for (int a = 0; a < 2; ++a) mbar_init(&res_bar[a], C::CHUNKS);
+        for (int a = 0; a < 2; ++a) { mbar_init(&res_bar[a], C::CHUNKS); mbar_init(&par_bar[a], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_base_smem, C::TMEM_COLS);
@@ -536,6 +537,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         const uint32_t S = smem_u32(slab_all + half * CHUNKS * C::CHUNK_BYTES);   // the group's slab: CHUNKS x [128 rows][128 B], swizzled
         const uint32_t par = smem_u32(par_all + half * 2 * HALF);             // the group's scale[HALF] | shift[HALF]
         uint64_t* const rbar = &res_bar[half];
+        uint64_t* const pbar = &par_bar[half];
         // swizzled address of 16-byte piece c (4 channels) of this warp's pixel row r (0..31) in chunk q
         auto slab_addr = [&](int q, int r, int c) -> uint32_t {
             return S + q * C::CHUNK_BYTES + (quarter * 32 + r) * 128 + ((c ^ (r & 7)) << 4);
@@ -557,13 +559,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 const int ho = ho0 + (prow >> p.bw_log2), wo = wo0 + (prow & (BW - 1));
                 return (ho < p.Ho && wo < p.Wo) ? (img * p.Ho + ho) * p.Wo + wo : -1;
             };
-            // ---- after the first K-block: decode the tile; fetch the group's folded-BN shift (the scale is folded into the
-            //      weights; arrays are padded to cout_pad >= n0 + HALF) asynchronously - every warp of the group issues the
-            //      same 16-byte copies (lanes [0, HALF/4)) and later waits for its own, so no barrier has to publish them;
-            //      safe to overwrite: every warp has passed the pre-store barrier of the previous tile.  Then: the
-            //      previous tile's bulk stores have released the slab (waited for by the threads that issued them, published
-            //      by one group barrier), and the residual chunks (128 pixels x 32 channels each) stream into the slab while
-            //      the K loop runs.
+            // ---- after the first K-block (tiles with a long K loop): decode the tile and fetch the group's folded-BN shift (the
+            //      scale is folded into the weights; arrays are padded to cout_pad >= n0 + HALF) - safe to overwrite: every
+            //      warp has passed the pre-store barrier of the previous tile, and with it its add_shift.  Then: the previous
+            //      tile's bulk stores have released the slab (waited for by the threads that issued them, published by one
+            //      group barrier), and the residual chunks (128 pixels x 32 channels each) stream into the slab while the K
+            //      loop runs.
             // Tiles with a short K loop (<= 4 K-blocks, e.g. the bottleneck 1x1 convs) decode and fetch their folded-BN shift
             // at the TOP of the tile (with one K-block there is no second drain to hide the fetch behind).  The residual
             // prefetch stays behind the first drain's group barrier: issuing it at the top of the tile as well (right after
@@ -572,9 +573,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             // profiles/diag_noise.py) - a hazard on the slab that only the group barrier closes.  FCP_TC_ABLATE=32 re-enables
             // it for measurements.
             const bool early = kblocks <= 4 && (!has_res || p.res_tma) && !(p.ablate & 8);
+            // one thread per group copies the tile's HALF shift values (a bulk copy that completes on par_bar: single writer,
+            // every reader waits for the barrier phase - the previous scheme, identical cp.async copies by all four warps,
+            // was a benign but real write-write race that compute-sanitizer racecheck reports)
             auto fetch_params = [&]() {
-                if (lane < HALF / 4)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(par + lane * 16), "l"(p.shift + n0 + lane * 4) : "memory");
+                if (lane == 0 && quarter == 0) {
+                    mbar_expect_tx(pbar, HALF * 4);
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(par), "l"(p.shift + n0), "r"(HALF * 4), "r"(smem_u32(pbar)) : "memory");
+                }
             };
             auto fetch_residual = [&]() {
                 if (has_res && p.res_tma && dma) {
@@ -629,7 +636,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             // acc += shift (per channel; the weights carry the folded-BN scale): needs the params fetched after the first
             // K-block, so it rides on the second K-block's drain
             auto add_shift = [&]() {
-                asm volatile("cp.async.wait_all;" ::: "memory");
+                mbar_wait(pbar, tile_par);
                 __syncwarp();
 #pragma unroll
                 for (int j = 0; j < HALF; j += 4) {
