@@ -64,6 +64,8 @@ struct ConvOp {
     float post_scale2 = 1.f;
     const float* res3 = nullptr; int res3_cs = 0, res3_co = 0;              // added after (..)*post_scale2
     int a_exact = 0;           // the input values are small integers (u8 - mean): the split's low part is zero
+    // detector stem straight from the uint8 RGB batch [n, stem_h, stem_w, 3] (tcgen05 f16x3 kernel only; `in` is unused)
+    const uint8_t* stem_src = nullptr; int stem_h = 0, stem_w = 0;
     int impl = 0;              // 0 CUDA-core fp32, 1 tcgen05 3xTF32, 2 tcgen05 3xFP16 block-scaled
 };
 
@@ -190,6 +192,7 @@ int gather_meta_join(fcp_ctx* ctx);
 int launch_conv_ffma(fcp_ctx* ctx, const ConvOp& op);
 int launch_conv_tc(fcp_ctx* ctx, const ConvOp& op);
 bool conv_tc_supported(const ConvOp& op);
+bool conv_tc_stem_supported(const void* images, int h, int w);
 int run_conv(fcp_ctx* ctx, const ConvOp& op);
 
 // stem: 7x7/s2 conv (Cin=3 -> 64) + scale/shift + ReLU.  mode 0: src = u8 RGB NHWC, flipped to BGR and mean-subtracted

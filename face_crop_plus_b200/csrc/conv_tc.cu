@@ -72,6 +72,12 @@ struct alignas(64) TcParams {
     int N, Ho, Wo, Cout, Cin, KH, KW, stride, pad, stride_w, pad_w;   // stride / pad: vertical; *_w: horizontal
     int cin_p;                                 // channels per tap in the packed weight matrix (MODE 1: Cin rounded up to 64)
     int w_exp;                                 // MODE 1: the packed weights are w * 2^w_exp
+    // stem mode (MODE 1 only): the 7x7 / stride 2 / pad 3 detector stem straight from the uint8 RGB image.  The producer lands
+    // one uint8 halo tile per output tile (2*BH+5 rows x 6*BW+15 bytes + alignment slack, TMA, zero filled outside the image); the converters
+    // cut each pixel's 7 horizontal taps x 3 channels (21 contiguous bytes per tap row) out of it, subtract the channel
+    // means and write exact fp16 integers into tensor memory.  K-block b = tap rows 2b, 2b+1 (32 K slots each, 21 used).
+    CUtensorMap tmStem;
+    int stem, stem_H, stem_W, stem_box_w, stem_box_h;
     int a_exact;                               // the activations are exactly representable in 11 significant bits (u8 - mean):
                                                //   a_lo == 0, the a_lo*w_hi MMAs are skipped
     int tiles_x, tiles_y, tiles_n, num_tiles, bw_log2, BH;
@@ -115,6 +121,10 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
@@ -134,6 +144,11 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
 }
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
@@ -335,6 +350,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     const int c0 = cc * C::KBLK, kcol = tap * p.cin_p + c0;
                     // the activation tile first (it has the longer way to go: landing -> converters -> tensor memory);
                     // MODE 1: two 32-channel boxes per K-block (the second one is skipped past the last channel)
+                    if (MODE && p.stem) {
+                        if (kb == 0) {
+                            mbar_wait<true>(&a_free[land], lphase ^ 1);
+                            mbar_expect_tx(&full_a[land], (uint32_t)(p.stem_box_w * p.stem_box_h));
+                            tma_load_3d(landing(land), &p.tmStem, &full_a[land], (6 * wo0 - 9) & ~15, 2 * ho0 - 3, img);   // TMA: 16-byte aligned innermost start
+                            if (++land == C::LANDINGS) { land = 0; lphase ^= 1; }
+                        }
+                    } else
 #pragma unroll
                     for (int hf = 0; hf < C::HALVES; ++hf) {
                         if (hf && c0 + 32 >= p.Cin) break;
@@ -452,6 +475,68 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     tc_fence_after();
                     tmem_st32(dst, hi);
                     tmem_st32(dst + 32, lo);
+                } else if (p.stem) {
+                    // ---- stem: this thread's output pixel (ty, tx) of the tile; K-block kb = tap rows 2kb, 2kb+1.  The 7 taps x 3
+                    //      channels of a tap row are 21 contiguous bytes of the uint8 halo tile; byte b becomes the fp16 integer
+                    //      b - mean exactly: 0x6400 | b is fp16(1024 + b), minus fp16(1024 + mean).  Memory order R,G,B with
+                    //      means 123,117,104 (the BGR flip of retinaface.py:450 lives in the packed weights).
+                    if (kb == 0) {
+                        mbar_wait<true>(&full_a[land], lphase);
+                        if (warp == 2 && lane == 0) TL(gc, 5);
+                    }
+                    const int m_tile = tile / p.tiles_n, rem = m_tile % tiles_per_img;
+                    const int ho0 = (rem / p.tiles_x) * p.BH, wo0 = (rem % p.tiles_x) * BW;
+                    const int ty = row >> p.bw_log2, tx = row & (BW - 1);
+                    const int ho = ho0 + ty, wo = wo0 + tx;
+                    const bool edge_x = 2 * wo0 - 3 < 0 || 2 * (wo0 + BW - 1) + 3 >= p.stem_W;        // tile-uniform
+                    uint32_t vb = 0x1FFFFFu;                                                           // valid window bytes (21 bits)
+                    if (edge_x) {
+                        vb = 0;
+#pragma unroll
+                        for (int sx = 0; sx < 7; ++sx) {
+                            const int xx = 2 * wo - 3 + sx;
+                            if (xx >= 0 && xx < p.stem_W) vb |= 7u << (3 * sx);
+                        }
+                    }
+                    const uint32_t tile_smem = smem_u32(landing(land));
+                    const __half2 c0 = __floats2half2_rn(1024.f + 123.f, 1024.f + 117.f), c1 = __floats2half2_rn(1024.f + 104.f, 1024.f + 123.f),
+                                  c2 = __floats2half2_rn(1024.f + 117.f, 1024.f + 104.f);
+                    uint32_t hi[32];
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr) {
+                        const int r = 2 * kb + rr, y = 2 * ho + r - 3;
+                        const bool row_ok = r < 7 && y >= 0 && y < p.stem_H;
+                        const uint32_t a = tile_smem + (uint32_t)((2 * ty + r) * p.stem_box_w + ((6 * wo0 - 9) & 15) + 6 * tx);   // box starts at the aligned byte
+                        const uint32_t a4 = a & ~3u, sh = (a & 3u) * 8;
+                        uint32_t w[7];
+#pragma unroll
+                        for (int i = 0; i < 7; ++i) w[i] = r < 7 ? lds32(a4 + 4 * i) : 0u;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            uint32_t v = 0;
+                            if (j < 11) {
+                                const uint32_t q = __funnelshift_r(w[j >> 1], w[(j >> 1) + 1], sh);  // window bytes 4*(j>>1) .. +3
+                                const uint32_t pair = __byte_perm(q, 0x64646464u, (j & 1) ? 0x4342u : 0x4140u);   // (1024 + b_odd) << 16 | (1024 + b_even)
+                                const __half2 d = __hsub2(*reinterpret_cast<const __half2*>(&pair), j % 3 == 0 ? c0 : (j % 3 == 1 ? c1 : c2));
+                                v = *reinterpret_cast<const uint32_t*>(&d);
+                                uint32_t keep = ((vb >> (2 * j)) & 1u ? 0x0000FFFFu : 0u) | ((vb >> (2 * j + 1)) & 1u ? 0xFFFF0000u : 0u);
+                                if (!row_ok) keep = 0;
+                                v &= keep;
+                            }
+                            hi[16 * rr + j] = v;
+                        }
+                    }
+                    if (kb == kblocks - 1) {                                  // the halo tile is in registers for the last time: refill it
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&a_free[land]);
+                        if (++land == C::LANDINGS) { land = 0; lphase ^= 1; }
+                    }
+                    mbar_wait<true>(&empty[stage], phase ^ 1);                // the stage's TMEM slot: MMAs of K-block g - STAGES retired
+                    tc_fence_after();
+                    tmem_st16(dst, hi);
+                    tmem_st16(dst + 16, hi + 16);
+                    int ie = 127 - p.w_exp;                                   // the activations are unscaled integers: 1 / 2^w_exp
+                    tmem_st1(tmem_base + C::TMEM_SC0 + (gc & (C::SCALE_SLOTS - 1)) + lane_addr, (uint32_t)ie << 23);
                 } else {
                     // ---- block-scaled fp16 split of this thread's pixel row (64 channels, or 32 in a trailing half block)
                     const bool two = cc * C::KBLK + 32 < p.Cin;
@@ -814,12 +899,12 @@ EncodeTiledFn encode_fn() {
 }
 
 bool make_map(CUtensorMap* map, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box,
-              CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT32) {
+              CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     return fn(map, dtype, rank, base, dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+              swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <int BN, int MODE>
@@ -838,8 +923,14 @@ int launch(fcp_ctx* ctx, const TcParams& p) {
 
 }  // namespace
 
+// the uint8 stem route needs TMA-addressable image rows: 16-byte aligned base and row pitch
+bool conv_tc_stem_supported(const void* images, int h, int w) {
+    return encode_fn() != nullptr && (reinterpret_cast<uintptr_t>(images) & 15) == 0 && (w * 3) % 16 == 0 && h >= 8 && w >= 16 && h % 2 == 0 && w % 2 == 0;
+}
+
 bool conv_tc_supported(const ConvOp& op) {
     const ConvWeights& wt = *op.wt;
+    if (op.stem_src) return op.impl == 2 && wt.h_hi && wt.cout_pad == 64 && conv_tc_stem_supported(op.stem_src, op.stem_h, op.stem_w);
     if (wt.cin % KB != 0 || op.up_in) return false;
     const int stride_w = op.stride_w ? op.stride_w : op.stride;
     if ((op.stride != 1 && op.stride != 2) || (stride_w != 1 && stride_w != 2)) return false;
@@ -856,14 +947,20 @@ bool conv_tc_supported(const ConvOp& op) {
 int launch_conv_tc(fcp_ctx* ctx, const ConvOp& op) {
     const ConvWeights& wt = *op.wt;
     if (!conv_tc_supported(op)) return fail(ctx, FCP_ERR_INVALID, "conv_tc: unsupported shape");
-    if (op.in.c != wt.cin || op.out.c != wt.cout) return fail(ctx, FCP_ERR_INVALID, "conv: channel mismatch");
+    const bool stem = op.stem_src != nullptr;
+    if (!stem && (op.in.c != wt.cin || op.out.c != wt.cout)) return fail(ctx, FCP_ERR_INVALID, "conv: channel mismatch");
     TcParams p{};
-    const int H = op.in.h, W = op.in.w, cs = op.in.cs;
-    p.N = op.in.n; p.Ho = op.out.h; p.Wo = op.out.w; p.Cout = wt.cout; p.Cin = wt.cin;
+    const int H = stem ? op.stem_h : op.in.h, W = stem ? op.stem_w : op.in.w, cs = op.in.cs;
+    p.N = op.out.n; p.Ho = op.out.h; p.Wo = op.out.w; p.Cout = wt.cout; p.Cin = wt.cin;
     p.KH = wt.kh ? wt.kh : wt.k; p.KW = wt.kw ? wt.kw : wt.k;
     p.stride = op.stride; p.pad = op.pad;
     p.stride_w = op.stride_w ? op.stride_w : op.stride; p.pad_w = op.pad_w >= 0 ? op.pad_w : op.pad;
-    if ((H + 2 * p.pad - p.KH) / p.stride + 1 != p.Ho || (W + 2 * p.pad_w - p.KW) / p.stride_w + 1 != p.Wo)
+    if (stem) {
+        // K-block b of the packed weights = tap rows 2b, 2b+1 of the 7x7 kernel (4 K-blocks of 64): the kernel sees a 4x1 "conv"
+        if ((H + 6 - 7) / 2 + 1 != p.Ho || (W + 6 - 7) / 2 + 1 != p.Wo || op.out.c != 64) return fail(ctx, FCP_ERR_INVALID, "stem: output shape mismatch");
+        p.KH = 4; p.KW = 1; p.Cin = 64; p.stride = p.stride_w = 1; p.pad = p.pad_w = 0;
+        p.stem = 1; p.stem_H = H; p.stem_W = W;
+    } else if ((H + 2 * p.pad - p.KH) / p.stride + 1 != p.Ho || (W + 2 * p.pad_w - p.KW) / p.stride_w + 1 != p.Wo)
         return fail(ctx, FCP_ERR_INVALID, "conv: output shape mismatch");
     // spatial box of 128 output pixels: widest power-of-two width that does not overshoot the row by more than 2x
     int bw_log2 = 7;
@@ -872,6 +969,7 @@ int launch_conv_tc(fcp_ctx* ctx, const ConvOp& op) {
     int best = -1; size_t best_tiles = 0;
     for (int l = 3; l <= 7; ++l) {                            // pick the box with the fewest tiles (ties: squarer)
         int bw = 1 << l, bh = TILE_M / bw;
+        if (stem && l > 5) continue;                          // the uint8 halo box is 6*BW + 15 bytes wide (TMA: <= 256)
         size_t t = (size_t)((p.Wo + bw - 1) / bw) * ((p.Ho + bh - 1) / bh);
         if (best < 0 || t < best_tiles || (t == best_tiles && abs(l - 4) < abs(best - 4))) { best = l; best_tiles = t; }
     }
@@ -884,6 +982,16 @@ int launch_conv_tc(fcp_ctx* ctx, const ConvOp& op) {
     p.num_tiles = p.N * p.tiles_x * p.tiles_y * p.tiles_n;
     // ---- tensor maps
     float* base = op.in.p + op.in.co;
+    if (stem) {
+        p.stem_box_w = (15 + 6 * BW + 15 + 15) / 16 * 16;        // up to 15 bytes of alignment slack in front of the 6*BW + 15 window bytes
+        p.stem_box_h = 2 * BH + 5;
+        cuuint64_t dims[3] = {(cuuint64_t)W * 3, (cuuint64_t)H, (cuuint64_t)p.N};
+        cuuint64_t strides[2] = {(cuuint64_t)W * 3, (cuuint64_t)H * W * 3};
+        cuuint32_t box[3] = {(cuuint32_t)p.stem_box_w, (cuuint32_t)p.stem_box_h, 1};
+        if (p.stem_box_w > 256 || p.stem_box_h > 256 || p.stem_box_w * p.stem_box_h > A_TILE_BYTES ||
+            !make_map(&p.tmStem, const_cast<uint8_t*>(op.stem_src), 3, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_UINT8, CU_TENSOR_MAP_SWIZZLE_NONE))
+            return fail(ctx, FCP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the uint8 image");
+    } else
     for (int py = 0; py < p.stride; ++py)
         for (int px = 0; px < p.stride_w; ++px) {
             const int sh = p.stride, sw = p.stride_w;
@@ -898,7 +1006,7 @@ int launch_conv_tc(fcp_ctx* ctx, const ConvOp& op) {
     if (f16 && !wt.h_hi) return fail(ctx, FCP_ERR_INVALID, "conv_tc: this convolution has no fp16 packing");
     p.cin_p = f16 ? wt.cin_p : wt.cin;
     p.w_exp = wt.w_exp;
-    p.a_exact = op.a_exact;
+    p.a_exact = op.a_exact || stem;
     const cuuint64_t K = (cuuint64_t)p.KH * p.KW * p.cin_p;
     cuuint64_t bdims[2] = {K, (cuuint64_t)wt.cout_pad};
     cuuint64_t bstr[1] = {K * (f16 ? 2 : 4)};

@@ -83,6 +83,19 @@ static void stem7(Exec& ex, const std::string& name, const void* src, int mode, 
         if (!ex.dry) ex.status = launch_stem7(ex.ctx, src, mode, nb, h, w, stem->w_kn, stem->scale, stem->shift, out);
         return;
     }
+    // f16x3 mode, uint8 input (the detector): the converters read the image itself (one uint8 halo tile per output tile by TMA),
+    // no row-patch tensor exists.  The plan still budgets the row-patch route: it is the fallback for image pitches TMA
+    // cannot address (w*3 not a multiple of 16 bytes, unaligned batch).
+    const bool direct = mode == 0 && ex.ctx->use_tc == 2 && !getenv("FCP_STEM_ROWS") && ex.model->conv.count(name + ".direct") &&
+                        !ex.dry && conv_tc_stem_supported(src, h, w);
+    if (direct) {
+        ConvOp e;
+        e.stem_src = static_cast<const uint8_t*>(src); e.stem_h = h; e.stem_w = w;
+        Tensor in;                                     // unused by the stem route; carries the batch size
+        in.n = nb; in.h = h; in.w = w; in.c = in.cs = 64;
+        ex.conv(name + ".direct", in, out, 1, 0, FCP_ACT_RELU, e);
+        return;
+    }
     Tensor rows = ex.alloc(nb, h, out.w, 32);
     if (ex.ok() && !ex.dry) ex.status = launch_stem_rows(ex.ctx, src, mode, nb, h, w, rows);
     ConvOp e;
@@ -103,6 +116,7 @@ int finalize_retinaface(fcp_ctx* ctx) {
     Model& m = ctx->models[FCP_MODEL_RETINAFACE];
     FCP_TRY(pack_conv(ctx, m, {"body.conv1"}, "body.bn1", "body.conv1"));
     FCP_TRY(pack_stem_rows(ctx, m, "body.conv1", "body.conv1.rows"));
+    FCP_TRY(pack_stem_direct(ctx, m, "body.conv1", "body.conv1.direct"));
     const int blocks[4] = {3, 4, 6, 3};
     for (int li = 1; li <= 4; ++li)
         for (int b = 0; b < blocks[li - 1]; ++b) {

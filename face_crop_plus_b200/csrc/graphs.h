@@ -11,6 +11,8 @@ int pack_conv(fcp_ctx* ctx, Model& m, const std::vector<std::string>& convs, con
 // tensor-core packing of a 7x7 stem (`conv` = name of the already packed square conv, whose folded BN it shares):
 // weights [64][7 vertical taps][32 = 7 horizontal taps x 3 channels, zero padded], registered as `name`
 int pack_stem_rows(fcp_ctx* ctx, Model& m, const std::string& conv, const std::string& name);
+// tensor-core packing of the detector stem for the direct uint8 route (no row-patch tensor): [64][4 tap-row pairs][64]
+int pack_stem_direct(fcp_ctx* ctx, Model& m, const std::string& conv, const std::string& name);
 
 // borrowed input: used in place when it already lives on the device, otherwise copied H2D on the context stream
 class DevIn {

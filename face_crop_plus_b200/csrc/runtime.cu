@@ -268,6 +268,32 @@ int pack_stem_rows(fcp_ctx* ctx, Model& m, const std::string& conv, const std::s
     return FCP_OK;
 }
 
+// Direct uint8 stem (conv_tc.cu stem mode): K-block b of 64 = tap rows 2b, 2b+1 of the 7x7 kernel, 32 slots per tap row =
+// 7 horizontal taps x 3 channels in MEMORY order (R,G,B: the BGR flip of retinaface.py:450 is applied here), 21 used.
+int pack_stem_direct(fcp_ctx* ctx, Model& m, const std::string& conv, const std::string& name) {
+    const HostTensor* w = find(m, conv + ".weight");
+    auto it = m.conv.find(conv);
+    if (!w || w->shape.size() != 4 || w->shape[1] != 3 || w->shape[2] != 7 || w->shape[3] != 7 || it == m.conv.end())
+        return fail(ctx, FCP_ERR_STATE, "stem weights missing or not 7x7x3: " + conv);
+    ConvWeights cw = it->second;                       // shares scale / shift (folded BN) with the square packing
+    const std::vector<float>& scale = m.vec[conv + ".scale"];
+    if ((int)scale.size() < cw.cout || cw.cout_pad != 64) return fail(ctx, FCP_ERR_STATE, "stem scale missing: " + conv);
+    cw.cin = 64; cw.k = 7; cw.kh = 4; cw.kw = 1; cw.alg_k = 147;
+    cw.w_kn = cw.w_hi = cw.w_lo = nullptr;             // exists for the f16x3 tensor-core mode only
+    std::vector<float> wfull((size_t)cw.cout_pad * 4 * 64, 0.f);
+    for (int o = 0; o < cw.cout; ++o)
+        for (int r = 0; r < 7; ++r)
+            for (int sx = 0; sx < 7; ++sx)
+                for (int mch = 0; mch < 3; ++mch) {
+                    const int c = 2 - mch;             // conv input channel of memory channel mch (x[:, [2, 1, 0]])
+                    const float v = w->data[(((size_t)o * 3 + c) * 7 + r) * 7 + sx] * scale[o];
+                    wfull[((size_t)o * 4 + r / 2) * 64 + (r % 2) * 32 + sx * 3 + mch] = v;
+                }
+    FCP_TRY(pack_f16(ctx, cw, wfull, 4, 64));
+    m.conv[name] = cw;
+    return FCP_OK;
+}
+
 // ------------------------------------------------------------------------------------- host/device staging
 bool is_device_ptr(const void* p) {
     if (!p) return false;
@@ -338,7 +364,7 @@ int run_conv(fcp_ctx* ctx, const ConvOp& op) {
     const ConvWeights& w = *op.wt;
     const double M = (double)op.out.n * op.out.h * op.out.w, K = w.alg_k ? (double)w.alg_k : (double)w.k * w.k * w.cin;
     ctx->prof_flops += 2.0 * M * w.cout * K;
-    ctx->prof_bytes += 4.0 * ((double)op.in.pixels() * w.cin + M * w.cout + K * w.cout);
+    ctx->prof_bytes += (op.stem_src ? 3.0 * op.out.n * op.stem_h * op.stem_w : 4.0 * (double)op.in.pixels() * w.cin) + 4.0 * (M * w.cout + K * w.cout);
     ctx->prof_recs.push_back({(int)M, w.cout, w.alg_k ? 3 : w.cin, w.k, op.stride, tc ? 1 : 0});   // stems: the reference's 7x7x3
     return s;
 }

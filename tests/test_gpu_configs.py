@@ -199,3 +199,25 @@ def test_allgather_meta_single_rank_roundtrip(ctx):
     got = D.unpack_records(buf, 4)
     assert got["indices"] == (out["indices"] + 100).tolist() and np.array_equal(got["landmarks"], out["landmarks"])
     assert np.array_equal(got["matrices"], out["matrices"]) and np.array_equal(got["valid"], out["valid"].astype(bool))
+
+
+# ------------------------------------------------------------------------------------------------ detector stem
+def test_detector_stem_direct_uint8_route_equals_row_patch_route(ctx):
+    """The 7x7/2 detector stem read straight from the uint8 batch (TMA halo tiles, exact fp16 integers) against the row-patch
+    route (FCP_STEM_ROWS=1) and the CUDA-core stem: same network heads to float noise, on sizes with partial tiles at the
+    right/bottom edges, and on a pitch TMA cannot address (w*3 % 16 != 0: both settings take the row-patch route)."""
+    import os
+    for h, w in ((256, 320), (136, 208), (250, 314)):
+        imgs = synth.make_images(2, h, w, seed=60 + h)
+        direct = ctx.detect_heads(imgs)
+        os.environ["FCP_STEM_ROWS"] = "1"
+        try:
+            rows = ctx.detect_heads(imgs)
+        finally:
+            del os.environ["FCP_STEM_ROWS"]
+        ctx.set_conv_impl(0)
+        ffma = ctx.detect_heads(imgs)
+        ctx.set_conv_impl(2)
+        scale = float(np.abs(ffma).max())
+        print(f"stem routes {h}x{w}: |direct - rows| {np.abs(direct - rows).max():.2e}, |direct - cuda-core| {np.abs(direct - ffma).max():.2e} (|heads| max {scale:.1f})")
+        assert np.abs(direct - rows).max() < 2e-4 and np.abs(direct - ffma).max() < 5e-4
