@@ -46,6 +46,7 @@ SIGNATURES = {
     "fcp_align": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _i, _p, _i, _i, _i, _i, _p, _p, _p]),
     "fcp_align_list": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _i, _p, _i, _i, _i, _i, _p, _p, _p]),
     "fcp_reduce_landmarks": (_i, [_p, _p, _i, _i, _p]),
+    "fcp_set_cubic_mode": (_i, [_p, _i]),
     "fcp_as_batch": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "fcp_parse": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "fcp_parse_logits": (_i, [_p, _p, _i, _i, _i, _p]),
@@ -284,6 +285,11 @@ class Context:
         return out
 
     # ---- ingest
+    def set_cubic_mode(self, floating_point: bool):
+        """INTER_CUBIC arithmetic of :meth:`as_batch`: True (default) = what IPP-enabled cv2 builds compute, False = OpenCV's
+        own fixed-point code (``fcp_set_cubic_mode``)."""
+        self.check(self.lib.fcp_set_cubic_mode(self.h, int(bool(floating_point))))
+
     def as_batch(self, images, size=512, padding_mode="constant", out=None):
         """``utils.as_batch`` (utils.py:273-342) on the device: list of u8 [h_i,w_i,3] arrays (or CUDA uint8 tensors) ->
         (batch u8 [n,H,W,3], unscales f64 [n], paddings i64 [n,4]).  ``out``: optional preallocated batch (numpy array or

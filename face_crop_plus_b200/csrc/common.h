@@ -132,6 +132,9 @@ struct fcp_ctx {
     struct StageRec { int stage; cudaEvent_t a, b; };
     std::vector<StageRec> stage_recs;
     size_t stage_used = 0;
+    // INTER_CUBIC arithmetic of fcp_as_batch: true = floating point (what IPP-enabled cv2 builds compute), false = OpenCV's
+    // own 11-bit fixed-point code
+    bool cubic_float = true;
     // RRDBNet stage of fcp_pipeline (fcp_set_enhance): on/off + the min_face_factor threshold of rrdb.py:141 (any float: the
     // face factor of a mirrored / degenerate landmark set is negative)
     bool enh_enabled = false;

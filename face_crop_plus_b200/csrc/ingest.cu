@@ -11,6 +11,11 @@
 //                               vertical pass in float32 ((S0*b0 + (S1*b1 + (S2*b2 + S3*b3))), cvRound) for the first
 //                               8*floor(3*width/8) values of a row - what OpenCV's SSE code does - and in integers
 //                               ((v + 2^21) >> 22) for the tail
+//   INTER_CUBIC, float (default): what the opencv-python x86 wheels really compute for 8-bit images - they pass the call to
+//                               Intel IPP: the separable Keys cubic (a = -0.75, clamped taps) in floating point, rounded to
+//                               nearest.  Evaluated here in float64 (horizontal, then vertical; mul and add rounded
+//                               separately): one grey level off cv2-with-IPP in < 1e-5 of the bytes (the fixed-point
+//                               path above: 4.5 %).  fcp_set_cubic_mode(ctx, 0) selects OpenCV's own fixed-point code.
 //   copyMakeBorder            : constant 0 / replicate / reflect / wrap / reflect_101 (borderInterpolate)
 // One thread per output pixel (3 channels); the kernel is HBM-bound: it reads every source pixel about once (a few
 // times through L1/L2 for the overlapping taps) and writes 3 bytes per output pixel.
@@ -24,7 +29,7 @@ namespace fcp {
 
 namespace {
 
-enum { ING_COPY = 0, ING_AREA_2X2 = 1, ING_AREA_INT = 2, ING_AREA_GEN = 3, ING_CUBIC = 4 };
+enum { ING_COPY = 0, ING_AREA_2X2 = 1, ING_AREA_INT = 2, ING_AREA_GEN = 3, ING_CUBIC = 4, ING_CUBIC_FLOAT = 5 };
 
 struct IngestImage {
     const uint8_t* src;      // u8 [h, w, 3]
@@ -57,8 +62,9 @@ __device__ __forceinline__ uint8_t sat_u8(int v) { return (uint8_t)min(max(v, 0)
 //   ING_AREA_GEN: ti[xt + d], ti[xt + d + 1] = range of entries of destination column d in the entry arrays that start at
 //                 ti[xt + nw + 1 + e] (source index) and tf[... same index] (weight); same for rows with yt / nh.
 //   ING_CUBIC   : ti[xt + 5*d] = source offset of the second tap, ti[xt + 5*d + 1..4] = 11-bit weights; rows likewise.
+//   ING_CUBIC_FLOAT: ti[xt + d] = source offset of the second tap, td[xt*4 .. ] = four float64 weights per destination index
 __global__ void ingest_kernel(const IngestImage* __restrict__ imgs, const int* __restrict__ ti, const float* __restrict__ tf,
-                              int size_w, int size_h, int border_mode, uint8_t* __restrict__ out) {
+                              const double* __restrict__ td, int size_w, int size_h, int border_mode, uint8_t* __restrict__ out) {
     const int X = blockIdx.x * blockDim.x + threadIdx.x, Y = blockIdx.y * blockDim.y + threadIdx.y;
     if (X >= size_w || Y >= size_h) return;
     const IngestImage im = imgs[blockIdx.z];
@@ -106,6 +112,27 @@ __global__ void ingest_kernel(const IngestImage* __restrict__ imgs, const int* _
             else { a0 = __fadd_rn(a0, __fmul_rn(beta, b0)); a1 = __fadd_rn(a1, __fmul_rn(beta, b1)); a2 = __fadd_rn(a2, __fmul_rn(beta, b2)); }
         }
         dst[0] = sat_u8(__float2int_rn(a0)); dst[1] = sat_u8(__float2int_rn(a1)); dst[2] = sat_u8(__float2int_rn(a2));
+    } else if (im.mode == ING_CUBIC_FLOAT) {
+        const int sx0 = ti[im.xt + rx], sy0 = ti[im.yt + ry];
+        const double* cx = td + (size_t)(im.xt + rx) * 4;
+        const double* cy = td + (size_t)(im.yt + ry) * 4;
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint8_t* row = src + (size_t)min(max(sy0 - 1 + k, 0), im.h - 1) * W3;
+            double h0 = 0.0, h1 = 0.0, h2 = 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint8_t* s = row + min(max(sx0 - 1 + j, 0), im.w - 1) * 3;
+                h0 = __dadd_rn(h0, __dmul_rn((double)s[0], cx[j]));
+                h1 = __dadd_rn(h1, __dmul_rn((double)s[1], cx[j]));
+                h2 = __dadd_rn(h2, __dmul_rn((double)s[2], cx[j]));
+            }
+            v0 = __dadd_rn(v0, __dmul_rn(h0, cy[k]));
+            v1 = __dadd_rn(v1, __dmul_rn(h1, cy[k]));
+            v2 = __dadd_rn(v2, __dmul_rn(h2, cy[k]));
+        }
+        dst[0] = sat_u8(__double2int_rn(v0)); dst[1] = sat_u8(__double2int_rn(v1)); dst[2] = sat_u8(__double2int_rn(v2));
     } else {   // ING_CUBIC
         const int* xe = ti + im.xt + 5 * rx;
         const int* ye = ti + im.yt + 5 * ry;
@@ -184,6 +211,22 @@ void cubic_table(int ssize, int dsize, std::vector<int>& ti, std::vector<float>&
     }
 }
 
+// float64 Keys weights (interpolateCubic's formulas, A = -0.75) + source offset per destination index; ti and td advance together
+void cubic_table_f64(int ssize, int dsize, std::vector<int>& ti, std::vector<double>& td) {
+    const double scale = 1.0 / ((double)dsize / ssize);
+    td.resize(ti.size() * 4, 0.0);
+    for (int d = 0; d < dsize; ++d) {
+        const double f = (d + 0.5) * scale - 0.5;
+        const int sx = (int)std::floor(f);
+        const double x = f - sx, A = -0.75;
+        const double c0 = ((A * (x + 1) - 5 * A) * (x + 1) + 8 * A) * (x + 1) - 4 * A;
+        const double c1 = ((A + 2) * x - (A + 3)) * x * x + 1;
+        const double c2 = ((A + 2) * (1 - x) - (A + 3)) * (1 - x) * (1 - x) + 1;
+        ti.push_back(sx);
+        td.push_back(c0); td.push_back(c1); td.push_back(c2); td.push_back(1.0 - c0 - c1 - c2);
+    }
+}
+
 }  // namespace
 
 // utils.py:317-331: (new_w, new_h, unscale, paddings) of one image; python float arithmetic == C double arithmetic
@@ -201,7 +244,7 @@ void ingest_plan(int h, int w, int size_w, int size_h, int* nw, int* nh, double*
 int launch_ingest(fcp_ctx* ctx, const uint8_t* const* dev_ptrs, const int32_t* hs, const int32_t* ws, int n, int size_w,
                   int size_h, int border_mode, uint8_t* out, double* unscales, int32_t* paddings) {
     std::vector<IngestImage> imgs(n);
-    std::vector<int> ti; std::vector<float> tf;
+    std::vector<int> ti; std::vector<float> tf; std::vector<double> td;
     for (int i = 0; i < n; ++i) {
         IngestImage& im = imgs[i];
         im = IngestImage{};
@@ -225,6 +268,11 @@ int launch_ingest(fcp_ctx* ctx, const uint8_t* const* dev_ptrs, const int32_t* h
                 im.xt = (int)ti.size(); area_table(im.w, im.nw, sx, ti, tf);
                 im.yt = (int)ti.size(); area_table(im.h, im.nh, sy, ti, tf);
             }
+        } else if (ctx->cubic_float) {
+            im.mode = ING_CUBIC_FLOAT;
+            im.xt = (int)ti.size(); cubic_table_f64(im.w, im.nw, ti, td);
+            im.yt = (int)ti.size(); cubic_table_f64(im.h, im.nh, ti, td);
+            tf.resize(ti.size());
         } else {
             im.mode = ING_CUBIC;
             im.xt = (int)ti.size(); cubic_table(im.w, im.nw, ti, tf);
@@ -233,22 +281,26 @@ int launch_ingest(fcp_ctx* ctx, const uint8_t* const* dev_ptrs, const int32_t* h
         }
     }
     if (ti.empty()) { ti.push_back(0); tf.push_back(0.f); }
+    td.resize(ti.size() * 4, 0.0);
     // the area tables index the entry arrays relative to their own start: rebase is done in the kernel (xbase / ybase)
-    void *d_imgs = nullptr, *d_ti = nullptr, *d_tf = nullptr;
+    void *d_imgs = nullptr, *d_ti = nullptr, *d_tf = nullptr, *d_td = nullptr;
     FCP_CUDA(ctx, cudaMallocAsync(&d_imgs, sizeof(IngestImage) * n, ctx->stream));
     FCP_CUDA(ctx, cudaMallocAsync(&d_ti, sizeof(int) * ti.size(), ctx->stream));
     FCP_CUDA(ctx, cudaMallocAsync(&d_tf, sizeof(float) * tf.size(), ctx->stream));
+    FCP_CUDA(ctx, cudaMallocAsync(&d_td, sizeof(double) * td.size(), ctx->stream));
+    FCP_CUDA(ctx, cudaMemcpyAsync(d_td, td.data(), sizeof(double) * td.size(), cudaMemcpyHostToDevice, ctx->stream));
     FCP_CUDA(ctx, cudaMemcpyAsync(d_imgs, imgs.data(), sizeof(IngestImage) * n, cudaMemcpyHostToDevice, ctx->stream));
     FCP_CUDA(ctx, cudaMemcpyAsync(d_ti, ti.data(), sizeof(int) * ti.size(), cudaMemcpyHostToDevice, ctx->stream));
     FCP_CUDA(ctx, cudaMemcpyAsync(d_tf, tf.data(), sizeof(float) * tf.size(), cudaMemcpyHostToDevice, ctx->stream));
     const dim3 block(32, 8), grid((size_w + 31) / 32, (size_h + 7) / 8, n);
     ingest_kernel<<<grid, block, 0, ctx->stream>>>(static_cast<const IngestImage*>(d_imgs), static_cast<const int*>(d_ti),
-                                                    static_cast<const float*>(d_tf), size_w, size_h, border_mode, out);
+                                                    static_cast<const float*>(d_tf), static_cast<const double*>(d_td), size_w, size_h, border_mode, out);
     FCP_KERNEL_CHECK(ctx);
     FCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));              // the pageable host tables above must outlive the copies
     FCP_CUDA(ctx, cudaFreeAsync(d_imgs, ctx->stream));
     FCP_CUDA(ctx, cudaFreeAsync(d_ti, ctx->stream));
     FCP_CUDA(ctx, cudaFreeAsync(d_tf, ctx->stream));
+    FCP_CUDA(ctx, cudaFreeAsync(d_td, ctx->stream));
     return FCP_OK;
 }
 

@@ -399,6 +399,7 @@ int fcp_create(int device, fcp_ctx** out) {
     }
     const char* tc = getenv("FCP_CONV_IMPL");
     if (tc) ctx->use_tc = atoi(tc);
+    if (const char* cm = getenv("FCP_CUBIC")) ctx->cubic_float = std::string(cm) != "opencv" && std::string(cm) != "fixed";
     *out = ctx;
     return FCP_OK;
 }
@@ -503,6 +504,12 @@ int fcp_profile_stages(fcp_ctx* ctx, double* out_ms8) {
         else cudaGetLastError();
     }
     ctx->stage_used = 0;
+    return FCP_OK;
+}
+
+int fcp_set_cubic_mode(fcp_ctx* ctx, int floating_point) {
+    if (!ctx) return FCP_ERR_INVALID;
+    ctx->cubic_float = floating_point != 0;
     return FCP_OK;
 }
 

@@ -83,7 +83,12 @@ int fcp_finalize(fcp_ctx* ctx, int model, int rrdb_blocks);
  * aspect ratio - OpenCV's INTER_AREA arithmetic when max(h,w) > max(size), its INTER_CUBIC arithmetic otherwise, a plain
  * copy when the size already fits (utils.py:320,334) - and centred with copyMakeBorder semantics (utils.py:335;
  * border_mode = FCP_BORDER_*).  out_batch u8 [n,size_h,size_w,3] (host or device); out_unscales f64 [n] and
- * out_paddings i32 [n,4] = (top,bottom,left,right) are HOST arrays (either may be NULL). */
+ * out_paddings i32 [n,4] = (top,bottom,left,right) are HOST arrays (either may be NULL).
+ * INTER_CUBIC exists in two arithmetics (fcp_set_cubic_mode): 1 (default) = floating point, what the opencv-python x86
+ * wheels compute (they route 8-bit cubic resizes to Intel IPP; restated in float64: one grey level off in < 1e-5 of the
+ * bytes); 0 = OpenCV's own 11-bit fixed-point code (bit-exact vs cv2 with cv2.ipp.setUseIPP(False)).  FCP_CUBIC=opencv
+ * selects 0 for new contexts.  INTER_AREA and the borders are bit-exact vs cv2 either way. */
+int fcp_set_cubic_mode(fcp_ctx* ctx, int floating_point);
 int fcp_as_batch(fcp_ctx* ctx, const uint8_t* const* image_ptrs, const int32_t* hs, const int32_t* ws, int n,
                  int size_w, int size_h, int border_mode, uint8_t* out_batch, double* out_unscales,
                  int32_t* out_paddings);

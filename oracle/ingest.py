@@ -130,6 +130,47 @@ def resize_cubic(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
     return out.reshape(dh, dw, cn)
 
 
+def cubic_coeffs_f64(x: float) -> np.ndarray:
+    """``interpolateCubic`` (A = -0.75) in float64."""
+    A = -0.75
+    c0 = ((A * (x + 1) - 5 * A) * (x + 1) + 8 * A) * (x + 1) - 4 * A
+    c1 = ((A + 2) * x - (A + 3)) * x * x + 1
+    c2 = ((A + 2) * (1 - x) - (A + 3)) * (1 - x) * (1 - x) + 1
+    return np.array([c0, c1, c2, 1.0 - c0 - c1 - c2], dtype=np.float64)
+
+
+def resize_cubic_float(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    """``cv2.resize(..., INTER_CUBIC)`` as the opencv-python x86 wheels compute it for 8-bit images: they hand the call to
+    Intel IPP (closed source), whose result is the separable Keys cubic (a = -0.75, taps clamped to the border) evaluated in
+    floating point and rounded to nearest - NOT OpenCV's 11-bit fixed-point code.  This restatement evaluates it in float64
+    (horizontal pass, then vertical, products and sums rounded separately, round-half-even); measured against cv2 with IPP
+    on it differs by one grey level in < 1e-5 of the bytes (IPP's internal float32 order is not public), where the
+    fixed-point path differs in ~4.5 %.  tests/test_ingest_cpu.py::test_cubic_float_vs_ipp_build."""
+    sh, sw, cn = src.shape
+    if (dw, dh) == (sw, sh):
+        return src.copy()
+
+    def table(ssize, dsize):
+        scale = 1.0 / (dsize / ssize)
+        idx, cf = np.zeros((dsize, 4), np.int64), np.zeros((dsize, 4), np.float64)
+        for d in range(dsize):
+            fx = (d + 0.5) * scale - 0.5
+            sx = math.floor(fx)
+            cf[d] = cubic_coeffs_f64(fx - sx)
+            idx[d] = np.clip(np.arange(sx - 1, sx + 3), 0, ssize - 1)
+        return idx, cf
+    xi, xc = table(sw, dw)
+    yi, yc = table(sh, dh)
+    s = src.astype(np.float64)
+    hor = np.zeros((sh, dw, cn), np.float64)
+    for k in range(4):
+        hor = hor + s[:, xi[:, k]] * xc[None, :, k, None]
+    out = np.zeros((dh, dw, cn), np.float64)
+    for k in range(4):
+        out = out + hor[yi[:, k]] * yc[:, k, None, None]
+    return np.clip(np.rint(out), 0, 255).astype(np.uint8)
+
+
 # ---------------------------------------------------------------------------------------------------- border
 def copy_make_border(img: np.ndarray, top: int, bottom: int, left: int, right: int, mode: str | int = "constant") -> np.ndarray:
     """``cv2.copyMakeBorder`` (constant value 0)."""
@@ -157,8 +198,9 @@ def plan(h: int, w: int, size: tuple[int, int]):
     return nw, nh, unscale, pad, interp
 
 
-def as_batch(images, size=512, padding_mode: str = "constant"):
-    """``as_batch`` (utils.py:273-342): (batch u8 [N,H,W,3], unscales f64 [N], paddings i64 [N,4])."""
+def as_batch(images, size=512, padding_mode: str = "constant", cubic: str = "fixed"):
+    """``as_batch`` (utils.py:273-342): (batch u8 [N,H,W,3], unscales f64 [N], paddings i64 [N,4]).  ``cubic``: "fixed" =
+    OpenCV's own INTER_CUBIC code (bit-exact vs cv2 with IPP off), "float" = the IPP build's (see resize_cubic_float)."""
     size = (size, size) if isinstance(size, int) else tuple(size)
     batch, unscales, paddings = [], [], []
     for img in images:
@@ -167,7 +209,7 @@ def as_batch(images, size=512, padding_mode: str = "constant"):
         if (nw, nh) == (w, h):
             res = img.copy()
         else:
-            res = resize_area(img, nw, nh) if interp == "area" else resize_cubic(img, nw, nh)
+            res = resize_area(img, nw, nh) if interp == "area" else (resize_cubic if cubic == "fixed" else resize_cubic_float)(img, nw, nh)
         batch.append(copy_make_border(res, *pad, mode=padding_mode))
         unscales.append(unscale)
         paddings.append(pad)

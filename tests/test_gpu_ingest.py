@@ -26,22 +26,33 @@ def test_as_batch_matches_oracle_all_paths(ctx, mode):
     shapes = [(150, 220), (128, 192), (192, 288), (40, 33), (64, 96), (31, 90), (200, 90), (9, 5), (97, 300), (64, 64)]
     imgs = _rand_images(shapes, 11)
     for size in [(96, 64), (64, 64), (80, 112)]:
-        got = ctx.as_batch(imgs, size, mode)
-        ref = ingest.as_batch(imgs, size, mode)
-        assert np.array_equal(got[0], ref[0]), f"{size} {mode}: {(got[0] != ref[0]).sum()} bytes differ"
-        assert np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+        for cubic in ("float", "fixed"):                       # both INTER_CUBIC arithmetics, each bit-exact vs its restatement
+            ctx.set_cubic_mode(cubic == "float")
+            got = ctx.as_batch(imgs, size, mode)
+            ref = ingest.as_batch(imgs, size, mode, cubic=cubic)
+            assert np.array_equal(got[0], ref[0]), f"{size} {mode} {cubic}: {(got[0] != ref[0]).sum()} bytes differ"
+            assert np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+    ctx.set_cubic_mode(True)
 
 
 def test_as_batch_vs_reference_golden(ctx):
     from oracle.make_golden_ingest import CONFIGS, images
     gold = np.load(__file__.rsplit("/", 1)[0] + "/golden/ingest.npz")
     imgs = images()
+    bad = tot = 0
     for ci, (size, mode) in enumerate(CONFIGS):
+        ctx.set_cubic_mode(False)
         batch, unscales, paddings = ctx.as_batch(imgs, size, mode)
         assert np.array_equal(batch, gold[f"c{ci}_cv_batch"])                   # OpenCV's own arithmetic: bit-exact
         assert np.array_equal(unscales, gold[f"c{ci}_unscales"]) and np.array_equal(paddings, gold[f"c{ci}_paddings"])
-        ipp = gold[f"c{ci}_cv_batch"].astype(np.int16) + gold[f"c{ci}_ipp_minus_cv"]
-        assert np.abs(batch.astype(np.int16) - ipp).max() <= 1                  # the IPP build of cv2 (cubic only): +-1
+        ctx.set_cubic_mode(True)                                                # default: the arithmetic of the IPP build
+        batch, _, _ = ctx.as_batch(imgs, size, mode)
+        ipp = gold[f"c{ci}_cv_batch"].astype(np.int16) + gold[f"c{ci}_ipp_minus_cv"]      # the reference as this image runs it
+        d = np.abs(batch.astype(np.int16) - ipp)
+        assert d.max() <= 1
+        bad += int((d > 0).sum()); tot += d.size
+    print(f"as_batch (float cubic) vs the reference's own outputs (IPP build of cv2): {bad} of {tot} bytes differ by one grey level")
+    assert bad / tot < 5e-5
 
 
 def test_as_batch_device_resident_in_and_out(ctx):
@@ -51,7 +62,7 @@ def test_as_batch_device_resident_in_and_out(ctx):
     dev = [torch.from_numpy(im).cuda() for im in imgs]
     out = torch.empty((3, 256, 256, 3), dtype=torch.uint8, device="cuda")
     got, _, pads = ctx.as_batch(dev, 256, "constant", out=out)
-    ref = ingest.as_batch(imgs, 256, "constant")
+    ref = ingest.as_batch(imgs, 256, "constant", cubic="float")
     assert got is out and np.array_equal(out.cpu().numpy(), ref[0]) and np.array_equal(pads, ref[2])
 
 

@@ -58,6 +58,24 @@ def test_cubic_vs_ipp_build_differs_by_at_most_one():
     assert d.max() <= 1 and (d > 0).mean() < 0.08
 
 
+def test_cubic_float_vs_ipp_build():
+    """The float restatement of INTER_CUBIC against cv2 as this image runs it (IPP on): enlargements and the reductions a
+    non-square target can ask for; at most one grey level off, in fewer than 5e-5 of the bytes (observed 7e-6)."""
+    cv2.ipp.setUseIPP(True)
+    rng = np.random.default_rng(8)
+    bad = tot = 0
+    for _ in range(24):
+        sh, sw = int(rng.integers(8, 140)), int(rng.integers(8, 140))
+        f = float(rng.uniform(0.7, 3.2))
+        dw, dh = max(4, int(sw * f)), max(4, int(sh * f))
+        img = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        ref = cv2.resize(img, (dw, dh), interpolation=cv2.INTER_CUBIC)
+        d = np.abs(ingest.resize_cubic_float(img, dw, dh).astype(int) - ref.astype(int))
+        assert d.max() <= 1, (sh, sw, dw, dh)
+        bad += int((d > 0).sum()); tot += d.size
+    assert bad / tot < 5e-5, bad / tot
+
+
 @pytest.mark.parametrize("mode", list(ingest.BORDER_MODES))
 def test_copy_make_border_vs_cv2(mode):
     rng = np.random.default_rng(5)
