@@ -106,6 +106,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// arrive that cannot be issued before `dep` has been computed: used to hand a TMA landing buffer back to the producer only
+// after the values loaded from it have really arrived in registers (an ld.shared is asynchronous; an arrive that merely
+// follows it in program order can overtake it, and the refill then races the load - seen as a few wrong 16-byte pieces of
+// single pixel rows, a few times per thousand launches)
+__device__ __forceinline__ void mbar_arrive_after(uint64_t* bar, uint32_t dep) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)), "r"(dep) : "memory");
+}
 template <bool BACKOFF = false>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done;
@@ -468,8 +475,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                             lo[4 * c + e] = __float_as_uint(__uint_as_float(w[e]) - __uint_as_float(hi[4 * c + e])) & 0xFFFFE000u;
                         }
                     }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&a_free[land]);                // the landing buffer is in registers: refill it
+                    uint32_t dep = 0;                                         // depends on all eight loads of every lane
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) dep |= hi[4 * c];
+                    dep = __reduce_or_sync(0xffffffffu, dep);
+                    if (lane == 0) mbar_arrive_after(&a_free[land], dep);     // the landing buffer is in registers: refill it
                     if (++land == C::LANDINGS) { land = 0; lphase ^= 1; }
                     mbar_wait<true>(&empty[stage], phase ^ 1);                // the stage's TMEM slot: MMAs of K-block g - STAGES retired
                     tc_fence_after();
@@ -526,9 +536,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                             hi[16 * rr + j] = v;
                         }
                     }
-                    if (kb == kblocks - 1) {                                  // the halo tile is in registers for the last time: refill it
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&a_free[land]);
+                    if (kb == kblocks - 1) {                                  // the halo tile has been read for the last time: refill it
+                        uint32_t dep = 0;                                     // (after the loads have really completed, see mbar_arrive_after)
+#pragma unroll
+                        for (int j = 0; j < 11; ++j) dep ^= hi[j] ^ hi[16 + j];
+                        dep = __reduce_or_sync(0xffffffffu, dep);
+                        if (lane == 0) mbar_arrive_after(&a_free[land], dep);
                         if (++land == C::LANDINGS) { land = 0; lphase ^= 1; }
                     }
                     mbar_wait<true>(&empty[stage], phase ^ 1);                // the stage's TMEM slot: MMAs of K-block g - STAGES retired
@@ -541,6 +554,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     // ---- block-scaled fp16 split of this thread's pixel row (64 channels, or 32 in a trailing half block)
                     const bool two = cc * C::KBLK + 32 < p.Cin;
                     float x[64];
+                    const int land0 = land;
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {
                         if (hf == 0 || two) {
@@ -553,8 +567,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                                 x[32 * hf + 4 * c] = __uint_as_float(q.x); x[32 * hf + 4 * c + 1] = __uint_as_float(q.y);
                                 x[32 * hf + 4 * c + 2] = __uint_as_float(q.z); x[32 * hf + 4 * c + 3] = __uint_as_float(q.w);
                             }
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&a_free[land]);        // the landing unit is in registers: refill it
                             if (++land == C::LANDINGS) { land = 0; lphase ^= 1; }
                         } else {
 #pragma unroll
@@ -570,6 +582,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                         m2 = fmaxf(m2, fabsf(x[j + 2])); m3 = fmaxf(m3, fabsf(x[j + 3]));
                     }
                     const uint32_t mbits = __float_as_uint(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+                    // the landing units are in registers now (the maximum depends on every loaded value): refill them
+                    const uint32_t all_loaded = __reduce_max_sync(0xffffffffu, mbits);
+                    if (lane == 0) {
+                        mbar_arrive_after(&a_free[land0], all_loaded);
+                        if (two) mbar_arrive_after(&a_free[land0 + 1 == C::LANDINGS ? 0 : land0 + 1], all_loaded);
+                    }
                     int e = (int)(mbits >> 23);                               // biased exponent of the row maximum (<= 254 for finite data)
                     e = e < 64 ? 64 : (e > 254 ? 254 : e);
                     const float sc = __uint_as_float((uint32_t)(268 - e) << 23);             // 2^(14 - (e - 127))
