@@ -54,8 +54,8 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=0, help="images per GPU (0 = the configuration's own)")
     ap.add_argument("--size", type=int, default=1024)
     ap.add_argument("--class-bias", type=float, default=4.8)
-    ap.add_argument("--det-mb", type=int, default=16)
-    ap.add_argument("--par-mb", type=int, default=32)
+    ap.add_argument("--det-mb", type=int, default=64)
+    ap.add_argument("--par-mb", type=int, default=128)
     ap.add_argument("--conv-impl", type=int, default=int(os.environ.get("FCP_CONV_IMPL", "2")))
     ap.add_argument("--cpu-sample", type=int, default=8, help="images in the cpu_baseline sample (0 = skip)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary configurations")

@@ -152,7 +152,7 @@ class Cropper:
         with _lock:
             bind_stream(self.ctx)
             if self.par_model is not None:
-                self.ctx.set_micro_batch(16, max(int(self.batch_size), 1))
+                self.ctx.set_micro_batch(32, max(int(self.batch_size), 1))
             batch = images if hasattr(images, "data_ptr") else np.ascontiguousarray(images)
             # enhancement (cropper.py:833-836) is a stage of the same call: gate, RRDBNet and the warp source stay on the device
             self.ctx.set_enhance(self.enh_model.min_face_factor if self.enh_model is not None else None)

@@ -112,7 +112,7 @@ struct fcp_ctx {
     bool own_stream = false;
     std::string error;
     int64_t launches = 0;
-    int det_mb = 16, par_mb = 32;
+    int det_mb = 32, par_mb = 64;
     fcp::Model models[3];
     fcp::Arena arena;          // activations
     fcp::Arena scratch;        // staging of host inputs/outputs, candidate buffers
@@ -151,7 +151,8 @@ struct fcp_ctx {
     // ahead of the compute stream (the hook runs at the top of every detector micro-batch)
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> copy_events;
-    std::function<int(int)> on_microbatch;
+    std::function<int(int)> on_microbatch;   // called with the micro-batch number at the top of every detector micro-batch
+    std::vector<int> mb_sched;               // detector micro-batch sizes installed by fcp_pipeline for that call (empty: uniform)
 };
 
 namespace fcp {

@@ -472,9 +472,22 @@ static int detect_core(fcp_ctx* ctx, const uint8_t* images, int n, int h, int w,
                        int max_faces, float* faces, int32_t* face_img, int32_t* face_count, float* heads_out) {
     Model* model = &ctx->models[FCP_MODEL_RETINAFACE];
     const int mb = std::min(ctx->det_mb, n);
+    // micro-batch schedule: uniform, or the one fcp_pipeline installed for host images (a short first micro-batch, so that
+    // the only exposed H2D copy is small)
+    std::vector<int> sched;
+    {
+        int total = 0;
+        for (int v : ctx->mb_sched) total += v;
+        if (!ctx->mb_sched.empty() && total == n) sched = ctx->mb_sched;
+        else for (int b0 = 0; b0 < n; b0 += mb) sched.push_back(std::min(mb, n - b0));
+    }
     std::vector<std::function<int(Exec&)>> plans;
-    for (int nb : {mb, n % mb})
-        if (nb > 0) plans.push_back([=](Exec& ex) { Tensor l[3]; return retinaface_forward(ex, nullptr, nb, h, w, l); });
+    {
+        std::vector<int> sizes(sched);
+        std::sort(sizes.begin(), sizes.end());
+        sizes.erase(std::unique(sizes.begin(), sizes.end()), sizes.end());
+        for (int nb : sizes) plans.push_back([=](Exec& ex) { Tensor l[3]; return retinaface_forward(ex, nullptr, nb, h, w, l); });
+    }
     FCP_TRY(plan_reserve(ctx, model, plans));
     const int A = det_num_priors(h, w), key_cap = det_key_capacity(h, w);
     float* rec = nullptr; unsigned long long* keys = nullptr; unsigned char* supp = nullptr; int32_t* counts = nullptr;
@@ -486,9 +499,10 @@ static int detect_core(fcp_ctx* ctx, const uint8_t* images, int n, int h, int w,
         FCP_CUDA(ctx, cudaMemsetAsync(face_count, 0, sizeof(int32_t), ctx->stream));
     }
     int status = FCP_OK;
-    for (int b0 = 0; b0 < n && status == FCP_OK; b0 += mb) {
-        int nb = std::min(mb, n - b0);
-        if (ctx->on_microbatch && (status = ctx->on_microbatch(b0)) != FCP_OK) break;
+    int b0 = 0;
+    for (size_t mi = 0; mi < sched.size() && status == FCP_OK; b0 += sched[mi], ++mi) {
+        const int nb = sched[mi];
+        if (ctx->on_microbatch && (status = ctx->on_microbatch((int)mi)) != FCP_OK) break;
         ctx->arena.reset();
         Exec ex{ctx, model, false};
         Tensor lvl[3];
@@ -1017,6 +1031,7 @@ int fcp_pipeline(fcp_ctx* ctx, const uint8_t* images, int n, int h, int w, const
         bool staged = false;
         ~Temps() {
             ctx->on_microbatch = nullptr;
+            ctx->mb_sched.clear();
             if (staged && ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);   // no copy may outlive its buffer
             for (void* p : ptrs) cudaFreeAsync(p, ctx->stream);
         }
@@ -1039,7 +1054,16 @@ int fcp_pipeline(fcp_ctx* ctx, const uint8_t* images, int n, int h, int w, const
     const uint8_t* dimg = images;
     if (!is_device_ptr(images)) {
         uint8_t* staged = nullptr;
-        const int mb = std::min(ctx->det_mb, n), chunks = (n + mb - 1) / mb;
+        // schedule: a first micro-batch of at most 16 images (its copy is the only one the compute stream has to wait for
+        // from cold), then det_mb images each; micro-batch c+1 is copied while micro-batch c computes
+        const int mb = std::min(ctx->det_mb, n);
+        std::vector<int> sched, start;
+        for (int b0 = 0; b0 < n;) {
+            const int nb = std::min(b0 == 0 && n > 16 ? std::min(mb, 16) : mb, n - b0);
+            start.push_back(b0); sched.push_back(nb); b0 += nb;
+        }
+        const int chunks = (int)sched.size();
+        ctx->mb_sched = sched;
         FCP_TRY(tmp.alloc((void**)&staged, img_bytes * n));
         if (!ctx->copy_stream) FCP_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         while ((int)ctx->copy_events.size() < chunks + 1) {
@@ -1050,16 +1074,15 @@ int fcp_pipeline(fcp_ctx* ctx, const uint8_t* images, int n, int h, int w, const
         FCP_CUDA(ctx, cudaEventRecord(ctx->copy_events[chunks], ctx->stream));              // the allocation is stream-ordered
         FCP_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_events[chunks], 0));
         tmp.staged = true;
-        auto issue = [ctx, images, staged, img_bytes, mb, n, chunks](int c) -> int {
+        auto issue = [ctx, images, staged, img_bytes, sched, start, chunks](int c) -> int {
             if (c >= chunks) return FCP_OK;
-            const size_t off = (size_t)c * mb * img_bytes, bytes = (size_t)std::min(mb, n - c * mb) * img_bytes;
+            const size_t off = (size_t)start[c] * img_bytes, bytes = (size_t)sched[c] * img_bytes;
             FCP_CUDA(ctx, cudaMemcpyAsync(staged + off, images + off, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
             FCP_CUDA(ctx, cudaEventRecord(ctx->copy_events[c], ctx->copy_stream));
             return FCP_OK;
         };
         FCP_TRY(issue(0));
-        ctx->on_microbatch = [ctx, issue, mb](int b0) -> int {
-            const int c = b0 / mb;
+        ctx->on_microbatch = [ctx, issue](int c) -> int {
             FCP_TRY(issue(c + 1));
             FCP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_events[c], 0));
             return FCP_OK;
@@ -1068,6 +1091,7 @@ int fcp_pipeline(fcp_ctx* ctx, const uint8_t* images, int n, int h, int w, const
     }
     FCP_TRY(detect_core(ctx, dimg, n, h, w, vis_threshold, nms_threshold, strategy, max_faces, faces, face_img, face_count, nullptr));
     ctx->on_microbatch = nullptr;
+    ctx->mb_sched.clear();
     // landmark un-pad (cropper.py:822) happens while unpacking the face records; the enhancement gate (rrdb.py:124-141)
     // is evaluated on the device from the un-padded landmarks and comes back with the face count in the one host sync
     DevOut lms, crops, mats, valid, lab, hist;

@@ -218,7 +218,7 @@ class BiSeNet(LoadMixin):
     def predict_u8(self, crops_u8_nhwc: np.ndarray):
         with _lock:
             bind_stream(self.ctx)
-            self.ctx.set_micro_batch(16, max(int(self.batch_size), 1))
+            self.ctx.set_micro_batch(32, max(int(self.batch_size), 1))
             labels, hist = self.ctx.parse(np.ascontiguousarray(crops_u8_nhwc))
         return self.groups_from(labels, hist)
 

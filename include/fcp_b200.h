@@ -53,7 +53,7 @@ int fcp_set_stream(fcp_ctx* ctx, void* cuda_stream);
 int fcp_sync(fcp_ctx* ctx);
 /* number of kernels this context has launched since creation (bench.py reports it as gpu_launches) */
 int64_t fcp_launch_count(const fcp_ctx* ctx);
-/* images per detector micro-batch / faces per parser micro-batch (bounds the activation arena; default 16 / 32) */
+/* images per detector micro-batch / faces per parser micro-batch (bounds the activation arena; default 32 / 64) */
 int fcp_set_micro_batch(fcp_ctx* ctx, int detect_images, int parse_faces);
 /* convolution kernel used by the model graphs: 2 = tcgen05 3xFP16 block-scaled split (default), 1 = tcgen05 3xTF32 split,
  * 0 = CUDA-core fp32; all three are fp32-accurate (error vs fp64 <= that of an fp32 FMA chain; tests/test_gpu_parity.py).
