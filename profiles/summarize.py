@@ -111,6 +111,9 @@ def launches2(src, shapes_log, dst, traffic_json=None):
             sw = 1 if kw == 1 and kh > 1 else st
             alg = 4.0 * (M * st * sw * cin + M * cout * (1 + res)) + (4 if impl == 2 else 8) * kh * kw * cin * cout
             key = f"k{kh}x{kw} s{st} cin{cin} cout{cout} M{M} res{res}"
+            if (kh, kw) == (4, 1):                        # the detector stem read from the uint8 image (conv_tc stem mode)
+                key = f"stem 7x7 s2 u8 RGB -> {cout} M{M}"
+                alg = 3.0 * M * 4 + 4.0 * M * cout + 4 * 256 * cout
             r = rows.setdefault(key, [0, 0.0, 0.0, 0.0, 0.0, 0.0])
             dram = d.get(R, 0) + d.get(W, 0)
             r[0] += 1; r[1] += d[T]; r[2] += alg; r[3] += dram; r[4] += 2.0 * M * cout * kh * kw * cin; r[5] += d.get(TP, 0) * d[T]
@@ -122,7 +125,7 @@ def launches2(src, shapes_log, dst, traffic_json=None):
         if traffic_json:
             json.dump({"kernel": "conv_tc_kernel", "dram_bytes_per_launch": tot_dram / len(conv), "algorithmic_bytes_per_launch": tot_alg / len(conv),
                        "launches": len(conv), "source": f"profiles/{dst.split('/')[-1]} (ncu dram__bytes_read.sum + dram__bytes_write.sum, average over "
-                                                        f"{len(conv)} consecutive convolution launches of a batch-16 step)"}, open(traffic_json, "w"), indent=1)
+                                                        f"{len(conv)} consecutive convolution launches, 64 images / 64 faces per launch)"}, open(traffic_json, "w"), indent=1)
     open(dst, "w").write("\n".join(lines) + "\n")
     print("\n".join(lines))
 
