@@ -474,7 +474,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                     "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (all convolution launches of the step)",
                                  "achieved": conv_tflops, "peak": tensor_peak, "unit": "TFLOP/s", "frac": conv_tflops / tensor_peak,
                                  "peak_source": f"{which} bf16 sustained (MEASURED_PEAKS.json); achieved = algorithmic fp32-equivalent FLOPs",
-                                 "traffic": traffic.get("dram_bytes_per_launch"), "traffic_source": traffic.get("source"),
+                                 "traffic": traffic.get("dram_bytes_per_launch"), "traffic_algorithmic": traffic.get("algorithmic_bytes_per_launch"),
+                                 "traffic_source": traffic.get("source"),
                                  "frac_of_split_ceiling": (conv_tflops / (tensor_peak / split)) if split else None,
                                  "split_ceiling_tflops": (tensor_peak / split) if split else None,
                                  "conv_launches_per_step": prof["conv_launches"] // args.steps,

@@ -1,0 +1,13 @@
+cd "${GRAFT_REPO_ROOT:-.}"; mkdir -p gpurun_out
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2_final_ref.jsonl 2> gpurun_out/r2_final_ref.err
+FCP_TRACE=1 timeout 900 python bench.py > gpurun_out/r2_final_bench.jsonl 2> gpurun_out/r2_final_trace.log
+python - <<PY
+import json
+d = json.loads(open("gpurun_out/r2_final_bench.jsonl").read().strip().splitlines()[-1])
+print("N=1 value", round(d["value"],1), "e2e", round(d["e2e"]["value"],1), "conv", round(d["roofline"]["achieved"],1), "clk", d["clocks"]["sm_mhz"], "stages", {k: round(v,1) for k,v in d["stages_ms"].items()})
+print("secondary", json.dumps(d["secondary"])[:1500])
+print("cpu", d.get("cpu_baseline"))
+r = json.loads(open("gpurun_out/r2_final_ref.jsonl").read().strip().splitlines()[-1])
+print("ref arm", r["value"], r["cpu_baseline"]["kind"], r["cpu_baseline"]["cores"])
+PY
+python __graft_entry__.py --smoke 2>&1 | tail -2
