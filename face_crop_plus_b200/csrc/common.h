@@ -43,9 +43,6 @@ struct ConvWeights {
     // tcgen05 kernel, f16x3 mode: w * scale * 2^w_exp split into fp16 hi + lo, K-major [cout_pad][taps * cin_p]
     void* h_hi = nullptr;
     void* h_lo = nullptr;
-    // same, halo packing of a 3x3 conv: K-major [cout_pad][cin/32][5 tap pairs][2 x 32 channels] (conv_tc.cu halo mode)
-    void* hh_hi = nullptr;
-    void* hh_lo = nullptr;
     int cin_p = 0;             // cin rounded up to 64 (one K-block = 64 channels)
     int w_exp = 0;
     float* scale = nullptr;    // device [cout_pad]

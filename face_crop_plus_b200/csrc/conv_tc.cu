@@ -78,12 +78,6 @@ struct alignas(64) TcParams {
     // means and write exact fp16 integers into tensor memory.  K-block b = tap rows 2b, 2b+1 (32 K slots each, 21 used).
     CUtensorMap tmStem;
     int stem, stem_H, stem_W, stem_box_w, stem_box_h;
-    // halo mode (MODE 1, 3x3 / stride 1 / pad 1): the producer lands ONE (BH+2) x (BW+2) pixel halo box per 32-channel block
-    // and output tile instead of nine shifted boxes; the converters read each tap's row out of it at a shifted address.
-    // K-block = (32-channel block, pair of taps): [tap 2t: 32 ch | tap 2t+1: 32 ch], 5 K-blocks per channel block (the
-    // last one holds tap 8 only).  The activation bytes fetched from L2 drop 6.4x - this kernel is L2-throughput bound.
-    CUtensorMap tmHalo;
-    int halo, halo_w;
     int a_exact;                               // the activations are exactly representable in 11 significant bits (u8 - mean):
                                                //   a_lo == 0, the a_lo*w_hi MMAs are skipped
     int tiles_x, tiles_y, tiles_n, num_tiles, bw_log2, BH;
@@ -335,7 +329,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     const uint32_t tmem_base = *tmem_base_smem;
 
     const int cchunks = (p.Cin + C::KBLK - 1) / C::KBLK;
-    const int kblocks = (MODE && p.halo) ? (p.Cin / 32) * 5 : p.KH * p.KW * cchunks;
+    const int kblocks = p.KH * p.KW * cchunks;
     const int BW = 1 << p.bw_log2;
     const int tiles_per_img = p.tiles_x * p.tiles_y;
 
@@ -360,18 +354,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                         map += px;
                         dx = (dx - px) >> 1;
                     }
-                    int c0 = cc * C::KBLK, kcol = tap * p.cin_p + c0;
-                    if (MODE && p.halo) kcol = kb * 64;                       // halo packing: K-blocks in launch order
+                    const int c0 = cc * C::KBLK, kcol = tap * p.cin_p + c0;
                     // the activation tile first (it has the longer way to go: landing -> converters -> tensor memory);
                     // MODE 1: two 32-channel boxes per K-block (the second one is skipped past the last channel)
-                    if (MODE && p.halo) {
-                        if (kb % 5 == 0) {                                    // halo units are pairs of landing units: 32 KiB each
-                            mbar_wait<true>(&a_free[land], lphase ^ 1);
-                            mbar_expect_tx(&full_a[land], (uint32_t)(p.halo_w * (p.BH + 2) * 128));
-                            tma_load_4d(landing(2 * land), &p.tmHalo, &full_a[land], (kb / 5) * 32, wo0 - 1, ho0 - 1, img);
-                            if (++land == C::LANDINGS / 2) { land = 0; lphase ^= 1; }
-                        }
-                    } else if (MODE && p.stem) {
+                    if (MODE && p.stem) {
                         if (kb == 0) {
                             mbar_wait<true>(&a_free[land], lphase ^ 1);
                             mbar_expect_tx(&full_a[land], (uint32_t)(p.stem_box_w * p.stem_box_h));
@@ -433,7 +419,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                         // one K-step = 8 tf32 | 16 fp16: +8 TMEM columns for A, +32 bytes (+2 in the addr>>4 field) inside B's
                         // swizzle span.  MODE 1: a K-block that starts within 32 channels of Cin only has 2 K-steps.
                         // Small terms first: while the accumulator is tiny its round-toward-zero losses are negligible.
-                        const int ksteps = (MODE && p.halo) ? (kb % 5 == 4 ? 2 : 4) : ((MODE && cc * C::KBLK + 32 >= p.Cin) ? 2 : 4);
+                        const int ksteps = (MODE && cc * C::KBLK + 32 >= p.Cin) ? 2 : 4;
                         if (!a_exact) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
@@ -566,37 +552,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     tmem_st1(tmem_base + C::TMEM_SC0 + (gc & (C::SCALE_SLOTS - 1)) + lane_addr, (uint32_t)ie << 23);
                 } else {
                     // ---- block-scaled fp16 split of this thread's pixel row (64 channels, or 32 in a trailing half block)
-                    const bool halo = p.halo != 0;
-                    const int tp = kb % 5;                                    // halo mode: pair of taps (2tp, 2tp+1) of this K-block
-                    const bool two = halo ? tp < 4 : cc * C::KBLK + 32 < p.Cin;
+                    const bool two = cc * C::KBLK + 32 < p.Cin;
                     float x[64];
                     const int land0 = land;
-                    if (halo && tp == 0) {
-                        mbar_wait<true>(&full_a[land], lphase);               // the channel block's halo box has landed
-                        if (warp == 2 && lane == 0) TL(gc, 5);
-                    }
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {
                         if (hf == 0 || two) {
-                            uint32_t src, rsw;                                // this thread's 128-byte row and its swizzle phase
-                            if (halo) {
-                                const int t = 2 * tp + hf, r = t / 3, sx = t - 3 * r;
-                                const int R = ((row >> p.bw_log2) + r) * p.halo_w + (row & (BW - 1)) + sx;   // halo pixel of tap (r, sx)
-                                src = smem_u32(landing(2 * land)) + (uint32_t)R * 128;
-                                rsw = (uint32_t)R & 7;
-                            } else {
-                                mbar_wait<true>(&full_a[land], lphase);
-                                if (hf == 0 && warp == 2 && lane == 0) TL(gc, 5);
-                                src = smem_u32(landing(land)) + row * 128;
-                                rsw = (uint32_t)row & 7;
-                                if (++land == C::LANDINGS) { land = 0; lphase ^= 1; }
-                            }
+                            mbar_wait<true>(&full_a[land], lphase);
+                            if (hf == 0 && warp == 2 && lane == 0) TL(gc, 5);
+                            const uint32_t src = smem_u32(landing(land)) + row * 128;
 #pragma unroll
                             for (int c = 0; c < 8; ++c) {
-                                const uint4 q = lds128(src + (uint32_t)((c ^ rsw) << 4));                 // logical 16-byte chunk c
+                                const uint4 q = lds128(src + (uint32_t)((c ^ (row & 7)) << 4));           // logical 16-byte chunk c
                                 x[32 * hf + 4 * c] = __uint_as_float(q.x); x[32 * hf + 4 * c + 1] = __uint_as_float(q.y);
                                 x[32 * hf + 4 * c + 2] = __uint_as_float(q.z); x[32 * hf + 4 * c + 3] = __uint_as_float(q.w);
                             }
+                            if (++land == C::LANDINGS) { land = 0; lphase ^= 1; }
                         } else {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) x[32 + j] = 0.f;
@@ -613,12 +584,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     const uint32_t mbits = __float_as_uint(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
                     // the landing units are in registers now (the maximum depends on every loaded value): refill them
                     const uint32_t all_loaded = __reduce_max_sync(0xffffffffu, mbits);
-                    if (halo) {
-                        if (tp == 4) {                                        // last tap of the channel block: hand the halo unit back
-                            if (lane == 0) mbar_arrive_after(&a_free[land], all_loaded);
-                            if (++land == C::LANDINGS / 2) { land = 0; lphase ^= 1; }
-                        }
-                    } else if (lane == 0) {
+                    if (lane == 0) {
                         mbar_arrive_after(&a_free[land0], all_loaded);
                         if (two) mbar_arrive_after(&a_free[land0 + 1 == C::LANDINGS ? 0 : land0 + 1], all_loaded);
                     }
@@ -1019,15 +985,9 @@ int launch_conv_tc(fcp_ctx* ctx, const ConvOp& op) {
     while (bw_log2 > 0 && (1 << bw_log2) >= 2 * p.Wo) --bw_log2;
     if (bw_log2 < 3) bw_log2 = 3;
     int best = -1; size_t best_tiles = 0;
-    // halo mode: 3x3 / stride 1 / pad 1 in the f16x3 mode - one (BH+2) x (BW+2) halo box per channel block instead of nine boxes
-    static const bool no_halo = getenv("FCP_NO_HALO") != nullptr;
-    // (measured: -40 % L2 bytes, +3-4 % on the Cout >= 128 layers, +2 % at Cout = 64; Cout = 32 layers lose - five drains per
-    //  32 channels instead of 4.5 - and keep the nine-box route)
-    const bool halo = op.impl == 2 && !stem && !no_halo && wt.hh_hi && p.KH == 3 && p.KW == 3 && p.stride == 1 && p.stride_w == 1 &&
-                      p.pad == 1 && p.pad_w == 1 && wt.cout_pad % 64 == 0;
     for (int l = 3; l <= 7; ++l) {                            // pick the box with the fewest tiles (ties: squarer)
         int bw = 1 << l, bh = TILE_M / bw;
-        if ((stem || halo) && l > 5) continue;                // uint8 halo box: 6*BW + 15 bytes wide (TMA: <= 256); f32 halo unit: <= 32 KiB
+        if (stem && l > 5) continue;                          // the uint8 halo box is 6*BW + 15 bytes wide (TMA: <= 256)
         size_t t = (size_t)((p.Wo + bw - 1) / bw) * ((p.Ho + bh - 1) / bh);
         if (best < 0 || t < best_tiles || (t == best_tiles && abs(l - 4) < abs(best - 4))) { best = l; best_tiles = t; }
     }
@@ -1049,13 +1009,6 @@ int launch_conv_tc(fcp_ctx* ctx, const ConvOp& op) {
         if (p.stem_box_w > 256 || p.stem_box_h > 256 || p.stem_box_w * p.stem_box_h > A_TILE_BYTES ||
             !make_map(&p.tmStem, const_cast<uint8_t*>(op.stem_src), 3, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_UINT8, CU_TENSOR_MAP_SWIZZLE_NONE))
             return fail(ctx, FCP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the uint8 image");
-    } else if (halo) {
-        p.halo = 1; p.halo_w = BW + 2;
-        cuuint64_t dims[4] = {(cuuint64_t)wt.cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)p.N};
-        cuuint64_t strides[3] = {(cuuint64_t)cs * 4, (cuuint64_t)W * cs * 4, (cuuint64_t)H * W * cs * 4};
-        cuuint32_t box[4] = {32, (cuuint32_t)(BW + 2), (cuuint32_t)(BH + 2), 1};
-        if ((BW + 2) * (BH + 2) * 128 > 2 * A_TILE_BYTES || !make_map(&p.tmHalo, base, 4, dims, strides, box))
-            return fail(ctx, FCP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the halo box");
     } else
     for (int py = 0; py < p.stride; ++py)
         for (int px = 0; px < p.stride_w; ++px) {
@@ -1072,13 +1025,13 @@ int launch_conv_tc(fcp_ctx* ctx, const ConvOp& op) {
     p.cin_p = f16 ? wt.cin_p : wt.cin;
     p.w_exp = wt.w_exp;
     p.a_exact = op.a_exact || stem;
-    const cuuint64_t K = halo ? (cuuint64_t)(wt.cin / 32) * 5 * 64 : (cuuint64_t)p.KH * p.KW * p.cin_p;
+    const cuuint64_t K = (cuuint64_t)p.KH * p.KW * p.cin_p;
     cuuint64_t bdims[2] = {K, (cuuint64_t)wt.cout_pad};
     cuuint64_t bstr[1] = {K * (f16 ? 2 : 4)};
     cuuint32_t bbox[2] = {(cuuint32_t)(f16 ? 64 : 32), (cuuint32_t)BN};
     const CUtensorMapDataType bt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-    if (!make_map(&p.tmBhi, halo ? wt.hh_hi : (f16 ? wt.h_hi : (void*)wt.w_hi), 2, bdims, bstr, bbox, bt) ||
-        !make_map(&p.tmBlo, halo ? wt.hh_lo : (f16 ? wt.h_lo : (void*)wt.w_lo), 2, bdims, bstr, bbox, bt))
+    if (!make_map(&p.tmBhi, f16 ? wt.h_hi : (void*)wt.w_hi, 2, bdims, bstr, bbox, bt) ||
+        !make_map(&p.tmBlo, f16 ? wt.h_lo : (void*)wt.w_lo, 2, bdims, bstr, bbox, bt))
         return fail(ctx, FCP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the weights");
     // ---- epilogue tensor maps: one box = the tile's 128 pixels x 32 channels (one chunk of an epilogue group)
     {

@@ -157,33 +157,6 @@ static int pack_f16(fcp_ctx* ctx, ConvWeights& cw, const std::vector<float>& wk,
     return FCP_OK;
 }
 
-// Halo packing of a 3x3 convolution for the f16x3 mode (same scale exponent as pack_f16, which must run first): the K axis is
-// ordered (32-channel block, tap pair, [tap 2t | tap 2t+1], channel) so that one K-block of 64 is two taps of one channel block -
-// both read out of one halo tile; the fifth pair of a block holds tap 8 and 32 zeros.
-static int pack_f16_halo(fcp_ctx* ctx, ConvWeights& cw, const std::vector<float>& wk, int cin) {
-    const int cblocks = cin / 32;
-    const size_t Kp = (size_t)cblocks * 5 * 64;
-    std::vector<__half> hi((size_t)cw.cout_pad * Kp, __float2half_rn(0.f)), lo(hi);
-    const float sc = std::ldexp(1.0f, cw.w_exp);
-    for (int o = 0; o < cw.cout_pad; ++o)
-        for (int cb = 0; cb < cblocks; ++cb)
-            for (int t = 0; t < 9; ++t)
-                for (int c = 0; c < 32; ++c) {
-                    const float v = wk[((size_t)o * 9 + t) * cin + cb * 32 + c] * sc;
-                    const size_t k = (size_t)o * Kp + ((size_t)cb * 5 + t / 2) * 64 + (t % 2) * 32 + c;
-                    const __half h = __float2half_rn(v);
-                    hi[k] = h;
-                    lo[k] = __float2half_rn(v - __half2float(h));
-                }
-    for (auto* pp : {&cw.hh_hi, &cw.hh_lo}) {
-        FCP_CUDA(ctx, cudaMalloc(pp, hi.size() * sizeof(__half)));
-        ctx->device_allocs.push_back(*pp);
-    }
-    FCP_CUDA(ctx, cudaMemcpy(cw.hh_hi, hi.data(), hi.size() * sizeof(__half), cudaMemcpyHostToDevice));
-    FCP_CUDA(ctx, cudaMemcpy(cw.hh_lo, lo.data(), lo.size() * sizeof(__half), cudaMemcpyHostToDevice));
-    return FCP_OK;
-}
-
 // Packs conv `convs[i].weight` (OIHW, concatenated along Cout) with optional bias and optional BatchNorm `bn`
 // (running stats folded like ATen's eval batch_norm: alpha = gamma/sqrt(var+eps), beta = bias - mean*alpha).
 int pack_conv(fcp_ctx* ctx, Model& m, const std::vector<std::string>& convs, const std::string& bn,
@@ -258,7 +231,6 @@ int pack_conv(fcp_ctx* ctx, Model& m, const std::vector<std::string>& convs, con
     FCP_TRY(upload(ctx, whi, &cw.w_hi));
     FCP_TRY(upload(ctx, wlo, &cw.w_lo));
     if (cw.cin % 32 == 0) FCP_TRY(pack_f16(ctx, cw, wfull, cw.k * cw.k, cw.cin));
-    if (cw.cin % 32 == 0 && cw.k == 3) FCP_TRY(pack_f16_halo(ctx, cw, wfull, cw.cin));
     FCP_TRY(upload(ctx, scale, &cw.scale));
     FCP_TRY(upload(ctx, shift, &cw.shift));
     m.conv[name] = cw;
