@@ -40,10 +40,10 @@ struct ConvWeights {
     float* w_kn = nullptr;     // device [k*k*cin][cout_pad]  (row = (r*k+s)*cin + c), CUDA-core kernel
     float* w_hi = nullptr;     // device [cout_pad][k*k*cin] K-major, tf32-truncated part   (tcgen05 kernel)
     float* w_lo = nullptr;     // device [cout_pad][k*k*cin] K-major, residual part          (tcgen05 kernel)
-    // tcgen05 kernel, f16x3 mode: w * scale * 2^w_exp split into fp16 hi + lo, K-major [cout_pad][taps * cin_p]
+    // tcgen05 kernel, f16x3 mode: w * scale * 2^w_exp split into fp16 hi + lo, K-major [cout_pad][taps * cin_p rounded up to 64]
     void* h_hi = nullptr;
     void* h_lo = nullptr;
-    int cin_p = 0;             // cin rounded up to 64 (one K-block = 64 channels)
+    int cin_p = 0;             // cin rounded up to 32 (K order: tap, channel; one K-block = two 32-channel units)
     int w_exp = 0;
     float* scale = nullptr;    // device [cout_pad]
     float* shift = nullptr;    // device [cout_pad]
@@ -57,6 +57,7 @@ struct ConvOp {
     int up_in = 0;             // read the input through a nearest x2 upsample (logical size = 2x physical)
     int act = FCP_ACT_NONE;
     float slope = 0.f;
+    int act_cols = 1 << 30;    // the activation applies to output channels < act_cols only (tcgen05 kernel; RRDBNet source-major passes)
     const float* res1 = nullptr; int res1_cs = 0, res1_co = 0;              // added before the activation
     float post_scale = 1.f;
     const float* res2 = nullptr; int res2_cs = 0, res2_co = 0;              // added after act*post_scale
@@ -66,7 +67,7 @@ struct ConvOp {
     int a_exact = 0;           // the input values are small integers (u8 - mean): the split's low part is zero
     // detector stem straight from the uint8 RGB batch [n, stem_h, stem_w, 3] (tcgen05 f16x3 kernel only; `in` is unused)
     const uint8_t* stem_src = nullptr; int stem_h = 0, stem_w = 0;
-    int impl = 0;              // 0 CUDA-core fp32, 1 tcgen05 3xTF32, 2 tcgen05 3xFP16 block-scaled
+    int impl = 0;              // 0 CUDA-core fp32, 1 tcgen05 3xTF32, 2 tcgen05 3xFP16 block-scaled, 3 = 2 without the correction terms
 };
 
 // ----------------------------------------------------------------------------------------------------------

@@ -70,7 +70,7 @@ struct alignas(64) TcParams {
     CUtensorMap tmOut, tmRes;                  // output / residual tensor, box = the tile's 128 pixels x 32 channels
     int out_tma, res_tma;                      // epilogue data paths: bulk tensor store / load usable for this launch
     int N, Ho, Wo, Cout, Cin, KH, KW, stride, pad, stride_w, pad_w;   // stride / pad: vertical; *_w: horizontal
-    int cin_p;                                 // channels per tap in the packed weight matrix (MODE 1: Cin rounded up to 64)
+    int cin_p;                                 // channels per tap in the packed weight matrix (MODE 1: Cin rounded up to 32)
     int w_exp;                                 // MODE 1: the packed weights are w * 2^w_exp
     // stem mode (MODE 1 only): the 7x7 / stride 2 / pad 3 detector stem straight from the uint8 RGB image.  The producer lands
     // one uint8 halo tile per output tile (2*BH+5 rows x 6*BW+15 bytes + alignment slack, TMA, zero filled outside the image); the converters
@@ -78,6 +78,8 @@ struct alignas(64) TcParams {
     // means and write exact fp16 integers into tensor memory.  K-block b = tap rows 2b, 2b+1 (32 K slots each, 21 used).
     CUtensorMap tmStem;
     int stem, stem_H, stem_W, stem_box_w, stem_box_h;
+    int act_cols;                              // channels >= act_cols skip the activation (general epilogue form only)
+    int single;                                // opt-in fast mode: hi x hi only (one pass, 11 significant bits per operand)
     int a_exact;                               // the activations are exactly representable in 11 significant bits (u8 - mean):
                                                //   a_lo == 0, the a_lo*w_hi MMAs are skipped
     int tiles_x, tiles_y, tiles_n, num_tiles, bw_log2, BH;
@@ -328,8 +330,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
 
-    const int cchunks = (p.Cin + C::KBLK - 1) / C::KBLK;
-    const int kblocks = p.KH * p.KW * cchunks;
+    // K runs over 32-channel units in (tap, channel) order; a K-block is HALVES consecutive units, so with Cin = 32, 96,
+    // 160 ... a MODE 1 K-block pairs the last unit of one tap with the first of the next instead of carrying an empty half
+    // (the packed weight matrix has the same order: pack_f16).  Only the very last K-block of a tile can be half empty.
+    const int upt = (p.Cin + 31) >> 5;                                    // units per tap
+    const int units = p.KH * p.KW * upt;
+    const int kblocks = (units + C::HALVES - 1) / C::HALVES;
     const int BW = 1 << p.bw_log2;
     const int tiles_per_img = p.tiles_x * p.tiles_y;
 
@@ -341,44 +347,44 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
                 const int img = m_tile / tiles_per_img, rem = m_tile - img * tiles_per_img;
                 const int ho0 = (rem / p.tiles_x) * p.BH, wo0 = (rem % p.tiles_x) * BW;
-                int tap = 0, cc = 0, r = 0, sx = 0;                          // K-block = (tap (r, sx), 32-channel chunk cc)
+                int tap = 0, ch = 0, r = 0, sx = 0;                          // next unit = (tap (r, sx), 32-channel chunk ch)
                 for (int kb = 0; kb < kblocks; ++kb) {
-                    int dy = r - p.pad, dx = sx - p.pad_w, map = 0;
-                    if (p.stride == 2) {   // input row 2*ho + dy lives in parity view (dy & 1) at row ho + (dy - (dy & 1)) / 2
-                        const int py = dy & 1;
-                        map = py * 2;
-                        dy = (dy - py) >> 1;
-                    }
-                    if (p.stride_w == 2) {
-                        const int px = dx & 1;
-                        map += px;
-                        dx = (dx - px) >> 1;
-                    }
-                    const int c0 = cc * C::KBLK, kcol = tap * p.cin_p + c0;
+                    const int kcol = tap * p.cin_p + ch * 32;
                     // the activation tile first (it has the longer way to go: landing -> converters -> tensor memory);
-                    // MODE 1: two 32-channel boxes per K-block (the second one is skipped past the last channel)
-                    if (MODE && p.stem) {
-                        if (kb == 0) {
-                            mbar_wait<true>(&a_free[land], lphase ^ 1);
-                            mbar_expect_tx(&full_a[land], (uint32_t)(p.stem_box_w * p.stem_box_h));
-                            tma_load_3d(landing(land), &p.tmStem, &full_a[land], (6 * wo0 - 9) & ~15, 2 * ho0 - 3, img);   // TMA: 16-byte aligned innermost start
-                            if (++land == C::LANDINGS) { land = 0; lphase ^= 1; }
-                        }
-                    } else
+                    // MODE 1: two 32-channel boxes per K-block (the second one is missing in a trailing half block)
+                    if (MODE && p.stem && kb == 0) {
+                        mbar_wait<true>(&a_free[land], lphase ^ 1);
+                        mbar_expect_tx(&full_a[land], (uint32_t)(p.stem_box_w * p.stem_box_h));
+                        tma_load_3d(landing(land), &p.tmStem, &full_a[land], (6 * wo0 - 9) & ~15, 2 * ho0 - 3, img);   // TMA: 16-byte aligned innermost start
+                        if (++land == C::LANDINGS) { land = 0; lphase ^= 1; }
+                    }
 #pragma unroll
                     for (int hf = 0; hf < C::HALVES; ++hf) {
-                        if (hf && c0 + 32 >= p.Cin) break;
-                        mbar_wait<true>(&a_free[land], lphase ^ 1);
-                        if (hf == 0) TL(gp, 0);
-                        mbar_expect_tx(&full_a[land], A_TILE_BYTES);
-                        tma_load_4d(landing(land), &p.tmA[map], &full_a[land], c0 + 32 * hf, wo0 + dx, ho0 + dy, img);
-                        if (++land == C::LANDINGS) { land = 0; lphase ^= 1; }
+                        if (tap >= p.KH * p.KW) break;
+                        if (!(MODE && p.stem)) {
+                            int dy = r - p.pad, dx = sx - p.pad_w, map = 0;
+                            if (p.stride == 2) {   // input row 2*ho + dy lives in parity view (dy & 1) at row ho + (dy - (dy & 1)) / 2
+                                const int py = dy & 1;
+                                map = py * 2;
+                                dy = (dy - py) >> 1;
+                            }
+                            if (p.stride_w == 2) {
+                                const int px = dx & 1;
+                                map += px;
+                                dx = (dx - px) >> 1;
+                            }
+                            mbar_wait<true>(&a_free[land], lphase ^ 1);
+                            if (hf == 0) TL(gp, 0);
+                            mbar_expect_tx(&full_a[land], A_TILE_BYTES);
+                            tma_load_4d(landing(land), &p.tmA[map], &full_a[land], ch * 32, wo0 + dx, ho0 + dy, img);
+                            if (++land == C::LANDINGS) { land = 0; lphase ^= 1; }
+                        }
+                        if (++ch == upt) { ch = 0; ++tap; if (++sx == p.KW) { sx = 0; ++r; } }
                     }
                     mbar_wait<true>(&empty[stage], phase ^ 1);
                     mbar_expect_tx(&full_b[stage], ((p.ablate & 1) ? 1 : 2) * C::B_TILE_BYTES);
                     tma_load_2d(stage_b_hi(stage), &p.tmBhi, &full_b[stage], kcol, n_tile * BN);
                     if (!(p.ablate & 1)) tma_load_2d(stage_b_lo(stage), &p.tmBlo, &full_b[stage], kcol, n_tile * BN);
-                    if (++cc == cchunks) { cc = 0; ++tap; if (++sx == p.KW) { sx = 0; ++r; } }
                     TL(gp, 1); ++gp;
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -400,9 +406,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             uint32_t turn = 0, mine = 0;                                      // g % ISSUERS; K-blocks this thread has issued
             int stage = 0; uint32_t phase = 0;
             const uint32_t buf = me;
-            const bool a_exact = p.a_exact != 0;
+            const bool a_exact = p.a_exact != 0, single = p.single != 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                int cc = 0;
                 for (int kb = 0; kb < kblocks; ++kb, ++g) {
                     if (turn == me) {
                         // operands first (normally long complete), the partial-sum buffer last: its release by the drain
@@ -417,10 +422,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                         const uint32_t a_hi = tmem_base + C::TMEM_A0 + stage * 64, a_lo = a_hi + 32;   // A operand: tensor memory
                         const uint64_t b_hi = umma_desc(smem_u32(stage_b_hi(stage))), b_lo = umma_desc(smem_u32(stage_b_lo(stage)));
                         // one K-step = 8 tf32 | 16 fp16: +8 TMEM columns for A, +32 bytes (+2 in the addr>>4 field) inside B's
-                        // swizzle span.  MODE 1: a K-block that starts within 32 channels of Cin only has 2 K-steps.
+                        // swizzle span.  MODE 1: a trailing half block (odd number of 32-channel units) only has 2 K-steps.
                         // Small terms first: while the accumulator is tiny its round-toward-zero losses are negligible.
-                        const int ksteps = (MODE && cc * C::KBLK + 32 >= p.Cin) ? 2 : 4;
-                        if (!a_exact) {
+                        const int ksteps = (MODE && 2 * kb + 1 >= units) ? 2 : 4;
+                        if (single) {                                         // fast mode: no correction terms
+                        } else if (!a_exact) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 if (k < ksteps) {
@@ -435,7 +441,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                         }
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            if (k < ksteps) mma(d_tmem, a_hi + 8 * k, b_hi + 2 * k, 1);
+                            if (k < ksteps) mma(d_tmem, a_hi + 8 * k, b_hi + 2 * k, (k != 0) | !single);
                         umma_commit(&empty[stage]);                           // smem slot + TMEM A slot reusable once these MMAs retire
                         umma_commit(&d_full[buf]);                            // partial sum of this K-block complete
                         TL(g, 4);
@@ -443,7 +449,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     }
                     if (++turn == (uint32_t)C::ISSUERS) turn = 0;
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
-                    if (++cc == cchunks) cc = 0;
                 }
             }
         }
@@ -455,7 +460,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
         int stage = 0, land = 0; uint32_t phase = 0, lphase = 0; uint32_t gc = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-            int cc = 0;
             for (int kb = 0; kb < kblocks; ++kb) {
                 const uint32_t dst = tmem_base + C::TMEM_A0 + stage * 64 + lane_addr;
                 if constexpr (MODE == 0) {
@@ -552,7 +556,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     tmem_st1(tmem_base + C::TMEM_SC0 + (gc & (C::SCALE_SLOTS - 1)) + lane_addr, (uint32_t)ie << 23);
                 } else {
                     // ---- block-scaled fp16 split of this thread's pixel row (64 channels, or 32 in a trailing half block)
-                    const bool two = cc * C::KBLK + 32 < p.Cin;
+                    const bool two = 2 * kb + 1 < units;
                     float x[64];
                     const int land0 = land;
 #pragma unroll
@@ -617,7 +621,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                         }
                     }
                     tmem_st1(tmem_base + C::TMEM_SC0 + (gc & (C::SCALE_SLOTS - 1)) + lane_addr, (uint32_t)ie << 23);
-                    if (++cc == cchunks) cc = 0;
                 }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
@@ -804,13 +807,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             auto phase1 = [&](auto simple_tag) {
                 constexpr bool SIMPLE = decltype(simple_tag)::value;
                 const float lo_clamp = neg_slope == 0.f ? 0.f : -INFINITY;    // relu | none
-                auto fuse = [&](float x, const float rv) -> float {           // x = conv*scale + shift already
+                auto fuse = [&](float x, const float rv, const float ns) -> float {   // x = conv*scale + shift already
                     if constexpr (SIMPLE) {
                         if (has_res) x += rv;
                         return fmaxf(x, lo_clamp);
                     } else {
                         if (r_pre) x += rv;
-                        x = fmaxf(x, x * neg_slope) * post_scale;             // act in {none, relu, leaky}: 0 <= neg_slope <= 1
+                        x = fmaxf(x, x * ns) * post_scale;                    // act in {none, relu, leaky}: 0 <= ns <= 1
                         if (r_post) x += rv;
                         return x;
                     }
@@ -834,16 +837,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     Step nxt = cur;
                     if (j + 8 < HALF) nxt = load_step(j + 8);
                     float4 x0, x1;
-                    x0.x = fuse(acc[j], cur.r0.x); x0.y = fuse(acc[j + 1], cur.r0.y);
-                    x0.z = fuse(acc[j + 2], cur.r0.z); x0.w = fuse(acc[j + 3], cur.r0.w);
-                    x1.x = fuse(acc[j + 4], cur.r1.x); x1.y = fuse(acc[j + 5], cur.r1.y);
-                    x1.z = fuse(acc[j + 6], cur.r1.z); x1.w = fuse(acc[j + 7], cur.r1.w);
+                    const float ns = n0 + j < p.act_cols ? neg_slope : 1.f;   // channels past act_cols: no activation
+                    x0.x = fuse(acc[j], cur.r0.x, ns); x0.y = fuse(acc[j + 1], cur.r0.y, ns);
+                    x0.z = fuse(acc[j + 2], cur.r0.z, ns); x0.w = fuse(acc[j + 3], cur.r0.w, ns);
+                    x1.x = fuse(acc[j + 4], cur.r1.x, ns); x1.y = fuse(acc[j + 5], cur.r1.y, ns);
+                    x1.z = fuse(acc[j + 6], cur.r1.z, ns); x1.w = fuse(acc[j + 7], cur.r1.w, ns);
                     sts_f4(a0, x0);
                     sts_f4(a1, x1);
                     cur = nxt;
                 }
             };
-            if (post_scale == 1.f && !r_post && (neg_slope == 0.f || neg_slope == 1.f)) phase1(std::true_type{});
+            if (post_scale == 1.f && !r_post && (neg_slope == 0.f || neg_slope == 1.f) && p.act_cols >= p.Cout) phase1(std::true_type{});
             else phase1(std::false_type{});
             if (warp == 6 && lane == 0) TL(g - 1, 11);
             if (p.out_tma) {
@@ -948,7 +952,7 @@ bool conv_tc_stem_supported(const void* images, int h, int w) {
 
 bool conv_tc_supported(const ConvOp& op) {
     const ConvWeights& wt = *op.wt;
-    if (op.stem_src) return op.impl == 2 && wt.h_hi && wt.cout_pad == 64 && conv_tc_stem_supported(op.stem_src, op.stem_h, op.stem_w);
+    if (op.stem_src) return op.impl >= 2 && wt.h_hi && wt.cout_pad == 64 && conv_tc_stem_supported(op.stem_src, op.stem_h, op.stem_w);
     if (wt.cin % KB != 0 || op.up_in) return false;
     const int stride_w = op.stride_w ? op.stride_w : op.stride;
     if ((op.stride != 1 && op.stride != 2) || (stride_w != 1 && stride_w != 2)) return false;
@@ -995,8 +999,9 @@ int launch_conv_tc(fcp_ctx* ctx, const ConvOp& op) {
     const int BW = 1 << bw_log2, BH = TILE_M / BW;
     p.bw_log2 = bw_log2; p.BH = BH;
     p.tiles_x = (p.Wo + BW - 1) / BW; p.tiles_y = (p.Ho + BH - 1) / BH;
-    const int BN = wt.cout_pad % 128 == 0 ? 128 : (wt.cout_pad % 64 == 0 ? 64 : 32);
-    p.tiles_n = wt.cout_pad / BN;
+    // 96 output channels: one padded 128-wide tile (the activation tile is read once) instead of three 32-wide ones
+    const int BN = wt.cout_pad % 128 == 0 || wt.cout_pad == 96 ? 128 : (wt.cout_pad % 64 == 0 ? 64 : 32);
+    p.tiles_n = (wt.cout_pad + BN - 1) / BN;
     p.num_tiles = p.N * p.tiles_x * p.tiles_y * p.tiles_n;
     // ---- tensor maps
     float* base = op.in.p + op.in.co;
@@ -1020,12 +1025,14 @@ int launch_conv_tc(fcp_ctx* ctx, const ConvOp& op) {
             if (!make_map(&p.tmA[py * 2 + px], base + ((size_t)py * W + px) * cs, 4, dims, strides, box))
                 return fail(ctx, FCP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the activation tensor");
         }
-    const bool f16 = op.impl == 2;
+    const bool f16 = op.impl >= 2;
     if (f16 && !wt.h_hi) return fail(ctx, FCP_ERR_INVALID, "conv_tc: this convolution has no fp16 packing");
     p.cin_p = f16 ? wt.cin_p : wt.cin;
     p.w_exp = wt.w_exp;
     p.a_exact = op.a_exact || stem;
-    const cuuint64_t K = (cuuint64_t)p.KH * p.KW * p.cin_p;
+    p.single = op.impl == 3;
+    p.act_cols = op.act_cols;
+    const cuuint64_t K = f16 ? ((cuuint64_t)p.KH * p.KW * p.cin_p + 63) / 64 * 64 : (cuuint64_t)p.KH * p.KW * p.cin_p;
     cuuint64_t bdims[2] = {K, (cuuint64_t)wt.cout_pad};
     cuuint64_t bstr[1] = {K * (f16 ? 2 : 4)};
     cuuint32_t bbox[2] = {(cuuint32_t)(f16 ? 64 : 32), (cuuint32_t)BN};

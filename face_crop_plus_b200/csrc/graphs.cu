@@ -86,7 +86,7 @@ static void stem7(Exec& ex, const std::string& name, const void* src, int mode, 
     // f16x3 mode, uint8 input (the detector): the converters read the image itself (one uint8 halo tile per output tile by TMA),
     // no row-patch tensor exists.  The plan still budgets the row-patch route: it is the fallback for image pitches TMA
     // cannot address (w*3 not a multiple of 16 bytes, unaligned batch).
-    const bool direct = mode == 0 && ex.ctx->use_tc == 2 && !getenv("FCP_STEM_ROWS") && ex.model->conv.count(name + ".direct") &&
+    const bool direct = mode == 0 && ex.ctx->use_tc >= 2 && !getenv("FCP_STEM_ROWS") && ex.model->conv.count(name + ".direct") &&
                         !ex.dry && conv_tc_stem_supported(src, h, w);
     if (direct) {
         ConvOp e;
@@ -377,6 +377,61 @@ int finalize_rrdbnet(fcp_ctx* ctx) {
                 FCP_TRY(pack_conv(ctx, m, {p}, "", p));
             }
     for (const char* c : {"trunk_conv", "upconv1", "upconv2", "HRconv", "conv_last"}) FCP_TRY(pack_conv(ctx, m, {c}, "", c));
+    // ---- source-major packing of the dense blocks (rrdbnet_forward, tensor-core route).  ResidualDenseBlock_5C
+    // (_layers.py:179-186) is conv_k([x, x1 .. x_{k-1}]) for k = 1..5: conv_k's weight splits by input channel range into one
+    // block per SOURCE x_j, and one pass per source computes that source's contribution to every later conv at once.
+    //   s0a: x  -> [c1 c2 c3 c4]          (128)   bias 1-4, c1 final (leaky)
+    //   s0b: x  -> [c5]                   ( 64)   0.2 * (W5 x + b5), + x in the epilogue
+    //   s1a: x1 -> [c2 c3 c4 c5[0:32]]    (128)   accumulate, c2 final        s1b: x1 -> c5[32:64] (32)
+    //   s2 : x2 -> [c3 c4 c5]             (128)   accumulate, c3 final
+    //   s3 : x3 -> [c4 c5]                ( 96)   accumulate, c4 final
+    //   s4 : x4 -> next x                 ( 64)   + c5 = x + 0.2 * conv5(..)   (_layers.py:186)
+    // conv5's 0.2 is folded into its weight blocks (pack_conv's per-channel scale), so its partial sums accumulate pre-scaled.
+    struct Part { int conv, o0, o1; float scale; };
+    auto pack_source = [&](const std::string& prefix, const std::string& name, int c0, int c1, const std::vector<Part>& parts,
+                           bool with_bias) -> int {
+        HostTensor wt;
+        std::vector<float> scale, shift;
+        const int cn = c1 - c0;
+        for (const Part& pt : parts) {
+            const HostTensor* w = nullptr;
+            const HostTensor* b = nullptr;
+            {
+                const std::string cname = prefix + ".conv" + std::to_string(pt.conv);
+                auto iw = m.host.find(cname + ".weight");
+                auto ib = m.host.find(cname + ".bias");
+                if (iw == m.host.end() || iw->second.shape.size() != 4 || iw->second.shape[1] < c1 || iw->second.shape[0] < pt.o1 ||
+                    iw->second.shape[2] != 3 || iw->second.shape[3] != 3)
+                    return fail(ctx, FCP_ERR_STATE, "missing or mis-shaped dense-block weight: " + cname);
+                w = &iw->second;
+                if (ib != m.host.end()) b = &ib->second;
+            }
+            const int cin = (int)w->shape[1];
+            for (int o = pt.o0; o < pt.o1; ++o) {
+                for (int c = c0; c < c1; ++c)
+                    for (int t = 0; t < 9; ++t) wt.data.push_back(w->data[((size_t)o * cin + c) * 9 + t]);
+                scale.push_back(pt.scale);
+                shift.push_back(with_bias && b ? b->data[o] * pt.scale : 0.f);
+            }
+        }
+        wt.shape = {(int64_t)scale.size(), cn, 3, 3};
+        const std::string full = prefix + "." + name;
+        m.host[full + ".weight"] = std::move(wt);
+        int st = pack_conv(ctx, m, {full}, "", full, scale.data(), shift.data());
+        m.host.erase(full + ".weight");
+        return st;
+    };
+    for (int i = 0; i < m.rrdb_blocks; ++i)
+        for (int r = 1; r <= 3; ++r) {
+            const std::string p = "RRDB_trunk." + std::to_string(i) + ".RDB" + std::to_string(r);
+            FCP_TRY(pack_source(p, "s0a", 0, 64, {{1, 0, 32, 1.f}, {2, 0, 32, 1.f}, {3, 0, 32, 1.f}, {4, 0, 32, 1.f}}, true));
+            FCP_TRY(pack_source(p, "s0b", 0, 64, {{5, 0, 64, 0.2f}}, true));
+            FCP_TRY(pack_source(p, "s1a", 64, 96, {{2, 0, 32, 1.f}, {3, 0, 32, 1.f}, {4, 0, 32, 1.f}, {5, 0, 32, 0.2f}}, false));
+            FCP_TRY(pack_source(p, "s1b", 64, 96, {{5, 32, 64, 0.2f}}, false));
+            FCP_TRY(pack_source(p, "s2", 96, 128, {{3, 0, 32, 1.f}, {4, 0, 32, 1.f}, {5, 0, 64, 0.2f}}, false));
+            FCP_TRY(pack_source(p, "s3", 128, 160, {{4, 0, 32, 1.f}, {5, 0, 64, 0.2f}}, false));
+            FCP_TRY(pack_source(p, "s4", 160, 192, {{5, 0, 64, 0.2f}}, false));
+        }
     return FCP_OK;
 }
 
@@ -387,12 +442,17 @@ static int rrdbnet_forward(Exec& ex, const std::function<int(Tensor)>& fill_firs
     if (!cf) return ex.status;
     Tensor first = ex.alloc(nb, h, w, 64);
     if (ex.ok() && !ex.dry) ex.status = fill_first(first);
-    // three rotating 192-channel slabs [x | x1 | x2 | x3 | x4]: the dense concatenations of
-    // ResidualDenseBlock_5C (_layers.py:179-186) are channel-prefix views of one slab
+    // three rotating slabs [x | x1 | x2 | x3 | x4 (| c5)]: the dense concatenations of ResidualDenseBlock_5C
+    // (_layers.py:179-186) are channel-prefix views of one slab.  Tensor-core f16 route: source-major passes (see
+    // finalize_rrdbnet) - every x_j tile is read by ONE or two launches instead of by each of the 5 - j later convs, the
+    // partial sums of the not-yet-final convs accumulate in place in the slab (fp32, residual path of the conv epilogue).
+    // FCP_RRDB_LAYERWISE=1 keeps the conv-by-conv schedule (also the schedule of the 3xTF32 and CUDA-core routes).
+    const bool source_major = ex.ctx->use_tc >= 2 && !getenv("FCP_RRDB_LAYERWISE");
+    const int SC = source_major ? 256 : 192;
     Tensor slab[3];
-    for (auto& s : slab) s = ex.alloc(nb, h, w, 192);
+    for (auto& s : slab) s = ex.alloc(nb, h, w, SC);
     if (ex.ok() && !ex.dry)
-        ex.status = cudaMemcpy2DAsync(slab[0].p, 192 * sizeof(float), first.p, 64 * sizeof(float), 64 * sizeof(float),
+        ex.status = cudaMemcpy2DAsync(slab[0].p, SC * sizeof(float), first.p, 64 * sizeof(float), 64 * sizeof(float),
                                       first.pixels(), cudaMemcpyDeviceToDevice, ex.ctx->stream) == cudaSuccess
                         ? FCP_OK : fail(ex.ctx, FCP_ERR_CUDA, "slab init copy failed");
     int cur = 0;
@@ -402,6 +462,30 @@ static int rrdbnet_forward(Exec& ex, const std::function<int(Tensor)>& fill_firs
         for (int r = 0; r < 3; ++r) {
             std::string p = "RRDB_trunk." + std::to_string(i) + ".RDB" + std::to_string(r + 1);
             Tensor S = slab[order_in[r]], T = slab[order_out[r]];
+            if (source_major) {
+                auto acc_into = [&](Tensor dst, bool in_place, int act_cols) {       // (+ dst) -> dst, leaky on the first act_cols channels
+                    ConvOp o;
+                    o.slope = 0.2f;
+                    o.act_cols = act_cols;
+                    if (in_place) { o.res1 = dst.p; o.res1_cs = dst.cs; o.res1_co = dst.co; }
+                    return o;
+                };
+                ex.conv(p + ".s0a", S.slice(0, 64), S.slice(64, 128), 1, 1, FCP_ACT_LRELU, acc_into(S, false, 32));
+                ConvOp b0;                                                            // c5 = x + 0.2 * (W5[:, x] x + b5)
+                b0.res1 = S.p; b0.res1_cs = S.cs; b0.res1_co = S.co;
+                ex.conv(p + ".s0b", S.slice(0, 64), S.slice(192, 64), 1, 1, FCP_ACT_NONE, b0);
+                ex.conv(p + ".s1a", S.slice(64, 32), S.slice(96, 128), 1, 1, FCP_ACT_LRELU, acc_into(S.slice(96, 128), true, 32));
+                ex.conv(p + ".s1b", S.slice(64, 32), S.slice(224, 32), 1, 1, FCP_ACT_NONE, acc_into(S.slice(224, 32), true, 1 << 30));
+                ex.conv(p + ".s2", S.slice(96, 32), S.slice(128, 128), 1, 1, FCP_ACT_LRELU, acc_into(S.slice(128, 128), true, 32));
+                ex.conv(p + ".s3", S.slice(128, 32), S.slice(160, 96), 1, 1, FCP_ACT_LRELU, acc_into(S.slice(160, 96), true, 32));
+                ConvOp e = acc_into(S.slice(192, 64), true, 1 << 30);                      // next x = c5 + 0.2 * W5[:, x4] x4
+                if (r == 2) {                                                         // RRDB: out * 0.2 + x   (_layers.py:200)
+                    e.post_scale2 = 0.2f;
+                    e.res3 = slab[cur].p; e.res3_cs = SC; e.res3_co = 0;
+                }
+                ex.conv(p + ".s4", S.slice(160, 32), T.slice(0, 64), 1, 1, FCP_ACT_NONE, e);
+                continue;
+            }
             ConvOp lre;
             lre.slope = 0.2f;
             for (int c = 1; c <= 4; ++c)
@@ -412,7 +496,7 @@ static int rrdbnet_forward(Exec& ex, const std::function<int(Tensor)>& fill_firs
             e.res2 = S.p; e.res2_cs = S.cs; e.res2_co = 0;
             if (r == 2) {                               // RRDB: out * 0.2 + x   (_layers.py:200)
                 e.post_scale2 = 0.2f;
-                e.res3 = slab[cur].p; e.res3_cs = 192; e.res3_co = 0;
+                e.res3 = slab[cur].p; e.res3_cs = SC; e.res3_co = 0;
             }
             ex.conv(p + ".conv5", S, T.slice(0, 64), 1, 1, FCP_ACT_NONE, e);
         }

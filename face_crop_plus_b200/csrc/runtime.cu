@@ -136,8 +136,8 @@ static int pack_f16(fcp_ctx* ctx, ConvWeights& cw, const std::vector<float>& wk,
     int ew = 0;
     if (wmax > 0.f && std::isfinite(wmax)) std::frexp(wmax, &ew);        // wmax = m * 2^ew, 0.5 <= m < 1
     cw.w_exp = std::min(40, std::max(-40, 14 - ew));                     // wmax * 2^w_exp in [2^13, 2^14)
-    cw.cin_p = (cin + 63) / 64 * 64;
-    const size_t Kp = (size_t)taps * cw.cin_p;
+    cw.cin_p = (cin + 31) / 32 * 32;                                     // K order: (tap, channel), 32-channel units (conv_tc.cu)
+    const size_t Kp = ((size_t)taps * cw.cin_p + 63) / 64 * 64;          // whole K-blocks: a trailing half block reads zeros
     std::vector<__half> hi((size_t)cw.cout_pad * Kp, __float2half_rn(0.f)), lo(hi);
     const float sc = std::ldexp(1.0f, cw.w_exp);
     for (int o = 0; o < cw.cout_pad; ++o)
@@ -176,7 +176,8 @@ int pack_conv(fcp_ctx* ctx, Model& m, const std::vector<std::string>& convs, con
     cw.cout_pad = (cw.cout + 31) / 32 * 32;
     const int K = cw.k * cw.k * cw.cin;
     // ---- per-channel affine after the conv: conv bias, then BatchNorm (or the explicit scale/shift of the test hook)
-    std::vector<float> scale(cw.cout_pad, 1.f), shift(cw.cout_pad, 0.f);
+    const int vec_pad = (cw.cout_pad + 127) / 128 * 128;                 // the tcgen05 epilogue reads whole tile halves
+    std::vector<float> scale(vec_pad, 1.f), shift(vec_pad, 0.f);
     {
         int o0 = 0;
         for (size_t g = 0; g < ws.size(); ++g) {
@@ -341,6 +342,7 @@ DevOut::~DevOut() {
 int run_conv(fcp_ctx* ctx, const ConvOp& op) {
     const bool tc = op.impl >= 1 && conv_tc_supported(op);   // shapes the tensor-core kernel does not cover use the CUDA-core kernel
     if (!tc && !op.wt->w_kn) return fail(ctx, FCP_ERR_INVALID, "conv: this packing exists for the tensor-core kernel only");
+    if (!tc && op.act_cols < op.wt->cout) return fail(ctx, FCP_ERR_INVALID, "conv: a partial activation needs the tensor-core kernel");
     static const bool log_conv = getenv("FCP_LOG_CONV") != nullptr;      // one line per tensor-core launch, in launch order:
     if (log_conv && tc) {                                                  // lets an ncu capture (-k conv_tc -s N) be matched to layer shapes
         static long long seq = 0;
@@ -451,7 +453,7 @@ int fcp_set_micro_batch(fcp_ctx* ctx, int detect_images, int parse_faces) {
 }
 
 int fcp_set_conv_impl(fcp_ctx* ctx, int impl) {
-    if (!ctx || impl < 0 || impl > 2) return fail(ctx, FCP_ERR_INVALID, "conv impl must be 0, 1 or 2");
+    if (!ctx || impl < 0 || impl > 3) return fail(ctx, FCP_ERR_INVALID, "conv impl must be 0, 1, 2 or 3");
     ctx->use_tc = impl;
     return FCP_OK;
 }

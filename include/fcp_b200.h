@@ -57,6 +57,8 @@ int64_t fcp_launch_count(const fcp_ctx* ctx);
 int fcp_set_micro_batch(fcp_ctx* ctx, int detect_images, int parse_faces);
 /* convolution kernel used by the model graphs: 2 = tcgen05 3xFP16 block-scaled split (default), 1 = tcgen05 3xTF32 split,
  * 0 = CUDA-core fp32; all three are fp32-accurate (error vs fp64 <= that of an fp32 FMA chain; tests/test_gpu_parity.py).
+ * 3 = opt-in fast mode: the block-scaled FP16 kernel without its two correction terms (one tensor-core pass, 11 significant
+ * bits per operand, the accuracy class of cuDNN's TF32 path) - NOT inside the parity bar, never the default.
  * The environment variable FCP_CONV_IMPL sets the default of new contexts. */
 int fcp_set_conv_impl(fcp_ctx* ctx, int impl);
 

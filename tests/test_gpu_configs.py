@@ -38,6 +38,30 @@ def test_enhance_forward_256_vs_oracle(ctx):
     assert got.shape == (1, 3, 1024, 1024) and err < TOL
 
 
+def test_enhance_source_major_schedule_vs_layerwise_and_fp32(ctx):
+    """The tensor-core route runs every dense block source-major (one pass per x_j feeds all later convs, partial sums
+    accumulate in place - graphs.cu finalize_rrdbnet).  It must agree with the conv-by-conv schedule on the same kernel
+    and with the CUDA-core fp32 kernel (which always runs conv-by-conv) far inside the float32 tolerance, and odd sizes
+    (edge tiles, clipped TMA boxes) must behave."""
+    import os
+    x = torch.from_numpy(synth.make_images(2, 75, 52, seed=5)).permute(0, 3, 1, 2).float().contiguous().numpy() / 255
+    got = ctx.enhance_forward(x)
+    os.environ["FCP_RRDB_LAYERWISE"] = "1"
+    try:
+        layerwise = ctx.enhance_forward(x)
+    finally:
+        del os.environ["FCP_RRDB_LAYERWISE"]
+    ctx.set_conv_impl(0)
+    try:
+        fp32 = ctx.enhance_forward(x)
+    finally:
+        ctx.set_conv_impl(2)
+    e1, e2 = float(np.abs(got - layerwise).max()), float(np.abs(got - fp32).max())
+    print(f"source-major vs layerwise {e1:.3e}, vs CUDA-core fp32 {e2:.3e} (|y| max {np.abs(fp32).max():.3f})")
+    assert np.isfinite(got).all() and e1 < 1e-4 and e2 < 1e-4
+    assert not np.array_equal(got, layerwise)          # the switch really selects another schedule
+
+
 def test_enhance_u8_batched_equals_per_image_and_f32_path(ctx):
     """uint8 NHWC predict (the pipeline's form) == the float32 NCHW predict of rrdb.py:142-144, image by image, and the
     batched launches (5 gated images of 7 share launches) change nothing: images are independent."""

@@ -65,6 +65,9 @@ CONV_CASES = [  # (n, h, w, cin, cout, k, stride, pad, act, residual)
     (1, 96, 96, 32, 160, 3, 2, 1, "lrelu", False),    # general epilogue form, stride-2 parity views, cout_pad 160 -> BN 32
     (1, 24, 40, 160, 32, 3, 1, 1, "lrelu", False),    # f16x3: 2.5 K-blocks per tap (trailing 32-channel half block)
     (2, 48, 48, 128, 128, 3, 1, 1, "relu", False),    # BN = 128, 18 K-blocks of 64 channels
+    (1, 24, 40, 32, 96, 3, 1, 1, "lrelu", True),      # f16x3: K-blocks pair two taps (4.5 per tile); Cout 96 -> one padded 128-wide tile
+    (2, 20, 20, 96, 64, 1, 1, 0, "relu", False),      # 1x1 with three 32-channel units: 1.5 K-blocks
+    (1, 31, 45, 32, 32, 3, 2, 1, "none", False),      # unit pairs across taps with stride-2 parity views
 ]
 
 
@@ -105,6 +108,26 @@ def test_conv2d_tensor_core_accuracy_large_k(ctx):
     print("relative max error  cuda-core fp32: %.3e   tcgen05 3xTF32: %.3e   tcgen05 3xFP16 block-scaled: %.3e" % (err[0], err[1], err[2]))
     assert err[1] < 5e-6 and err[1] < 8 * max(err[0], 1e-7)
     assert err[2] < 5e-6 and err[2] < 8 * max(err[0], 1e-7)
+
+
+def test_conv2d_fast_mode_accuracy_class(ctx):
+    """impl 3 (opt-in, outside the parity bar): the block-scaled FP16 kernel without its correction terms.  Its error must
+    sit in the single-pass class - 11 significant bits per operand, ~2^-11 relative to sum |a||w| at worst and far less
+    after averaging over K - and well ABOVE the 3-term modes (i.e. the switch really does drop the correction terms)."""
+    g = torch.Generator().manual_seed(13)
+    n, h, w, cin, cout = 2, 32, 32, 256, 128
+    x = torch.randn((n, cin, h, w), generator=g)
+    wt = torch.randn((cout, cin, 3, 3), generator=g) * (2.0 / (cin * 9)) ** 0.5
+    ref = torch.nn.functional.conv2d(x.double(), wt.double(), None, 1, 1).permute(0, 2, 3, 1).numpy()
+    den = torch.nn.functional.conv2d(x.double().abs(), wt.double().abs(), None, 1, 1).permute(0, 2, 3, 1).numpy()
+    xin = x.permute(0, 2, 3, 1).contiguous().numpy()
+    err = {}
+    for impl in (2, 3):
+        got = ctx.conv2d(xin, wt.numpy(), 1, 1, impl=impl)
+        err[impl] = float(np.max(np.abs(got - ref) / den))
+    print("max |err| / sum|a||w|   3xFP16: %.3e   1xFP16 fast mode: %.3e" % (err[2], err[3]))
+    assert err[3] < 2.0 ** -11
+    assert err[3] > 20 * err[2]
 
 
 def test_conv2d_f16x3_dynamic_range(ctx):
