@@ -83,6 +83,7 @@ struct alignas(64) TcParams {
     int a_exact;                               // the activations are exactly representable in 11 significant bits (u8 - mean):
                                                //   a_lo == 0, the a_lo*w_hi MMAs are skipped
     int tiles_x, tiles_y, tiles_n, num_tiles, bw_log2, BH;
+    int pair_tiles;                            // PAIR kernels: tiles per CTA pair = tiles_n * ceil(m_tiles / 2)
     float* out; int out_cs, out_co;
     const float* scale; const float* shift;
     const float* res1; int res1_cs, res1_co;
@@ -219,6 +220,38 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
           "r"(r[30]), "r"(r[31])
         : "memory");
 }
+// PAIR kernels (cta_group::2: two CTAs of a cluster run one 256-row MMA, each holds half of the weight tile).
+// The weight load of either CTA completes its bytes on the LEADER's barrier (shared::cluster address with the peer bit cleared).
+__device__ __forceinline__ uint32_t leader_addr(const void* smem_ptr) { return smem_u32(smem_ptr) & 0xFEFFFFFFu; }
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(leader_addr(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// arrive on the leader CTA's copy of `bar` (converters / drain warps of both CTAs report to the one MMA issuer)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    uint32_t raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(raddr) : "r"(smem_u32(bar)));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+// MMA-retired signal to the same-offset barrier of both CTAs
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_f16_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t cols) {     // same warp id in both CTAs
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // arrives on `bar` when all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -291,7 +324,12 @@ template <int BN, int MODE> struct Cfg {
     static_assert(B_SLOT_BYTES % 1024 == 0 && B_TILE_BYTES % 1024 == 0, "operand tiles must stay 1024-byte aligned (swizzle atoms)");
 };
 
-template <int BN, int MODE>
+// PAIR = 1: launched as clusters of two CTAs (cta_group::2).  A pair works on two pixel tiles of the same output-channel
+// tile in lockstep: each CTA stages its own 128 pixel rows (activations -> converters -> its tensor memory) and HALF of
+// every weight tile; the leader CTA issues one 256 x BN MMA for both, the partial sums land in each CTA's tensor memory and
+// are drained and stored per CTA.  Per K-block an SM takes in 25 % fewer bytes (its weight tile is half as large) and the
+// tensor core reads half the weight bytes from its own shared memory.
+template <int BN, int MODE, int PAIR = 0>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
     using C = Cfg<BN, MODE>;
     extern __shared__ uint8_t smem_raw[];
@@ -318,17 +356,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     auto landing = [&](int l) { return smem + C::STAGES * C::B_SLOT_BYTES + l * A_TILE_BYTES; };
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_b[s], 1); mbar_init(&conv[s], 4); mbar_init(&empty[s], 1); }
+        // PAIR: full_b / conv / d_empty are only waited on in the leader CTA, where both CTAs' producers, converters and drain
+        // warps report; empty / d_full receive the leader's multicast commits in both CTAs
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_b[s], 1); mbar_init(&conv[s], PAIR ? 8 : 4); mbar_init(&empty[s], 1); }
         for (int l = 0; l < C::LANDINGS; ++l) { mbar_init(&full_a[l], 1); mbar_init(&a_free[l], 4); }
-        for (int a = 0; a < C::ISSUERS; ++a) { mbar_init(&d_full[a], 1); mbar_init(&d_empty[a], C::EPI_WARPS); }
+        for (int a = 0; a < C::ISSUERS; ++a) { mbar_init(&d_full[a], 1); mbar_init(&d_empty[a], (PAIR ? 2 : 1) * C::EPI_WARPS); }
         for (int a = 0; a < 2; ++a) { mbar_init(&res_bar[a], C::CHUNKS); mbar_init(&par_bar[a], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(tmem_base_smem, C::TMEM_COLS);
+    uint32_t cta_rank = 0;
+    if constexpr (PAIR) {
+        asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+        cluster_sync_all();                                               // both CTAs are resident, their barriers initialised
+        if (warp == 1) tmem_alloc_pair(tmem_base_smem, C::TMEM_COLS);
+    } else {
+        if (warp == 1) tmem_alloc(tmem_base_smem, C::TMEM_COLS);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
+    if constexpr (PAIR) cluster_sync_all();
+    // tile walk: a CTA (PAIR: a CTA pair) takes every tile_step-th tile; PAIR tile t = (n_tile, pixel tiles 2m, 2m+1)
+    const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int tile_end = PAIR ? p.pair_tiles : p.num_tiles;
+    auto m_tile_of = [&](int tile) { return PAIR ? 2 * (tile / p.tiles_n) + (int)cta_rank : tile / p.tiles_n; };
 
     // K runs over 32-channel units in (tap, channel) order; a K-block is HALVES consecutive units, so with Cin = 32, 96,
     // 160 ... a MODE 1 K-block pairs the last unit of one tap with the first of the next instead of carrying an empty half
@@ -343,8 +395,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         // ================================================================================== TMA producer
         if (lane == 0) {
             int stage = 0, land = 0; uint32_t phase = 0, lphase = 0; uint32_t gp = 0; (void)gp;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
+            for (int tile = tile0; tile < tile_end; tile += tile_step) {
+                const int n_tile = tile % p.tiles_n, m_tile = m_tile_of(tile);
                 const int img = m_tile / tiles_per_img, rem = m_tile - img * tiles_per_img;
                 const int ho0 = (rem / p.tiles_x) * p.BH, wo0 = (rem % p.tiles_x) * BW;
                 int tap = 0, ch = 0, r = 0, sx = 0;                          // next unit = (tap (r, sx), 32-channel chunk ch)
@@ -382,9 +434,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                         if (++ch == upt) { ch = 0; ++tap; if (++sx == p.KW) { sx = 0; ++r; } }
                     }
                     mbar_wait<true>(&empty[stage], phase ^ 1);
-                    mbar_expect_tx(&full_b[stage], ((p.ablate & 1) ? 1 : 2) * C::B_TILE_BYTES);
-                    tma_load_2d(stage_b_hi(stage), &p.tmBhi, &full_b[stage], kcol, n_tile * BN);
-                    if (!(p.ablate & 1)) tma_load_2d(stage_b_lo(stage), &p.tmBlo, &full_b[stage], kcol, n_tile * BN);
+                    if constexpr (PAIR) {   // my half of the output channels (BN/2 rows of w_hi and w_lo), bytes counted by the leader
+                        if (cta_rank == 0) mbar_expect_tx(&full_b[stage], 2 * C::B_TILE_BYTES);
+                        const int row = n_tile * BN + (int)cta_rank * (BN / 2);
+                        tma_load_2d_pair(stage_b_hi(stage), &p.tmBhi, &full_b[stage], kcol, row);
+                        tma_load_2d_pair(stage_b_lo(stage), &p.tmBlo, &full_b[stage], kcol, row);
+                    } else {
+                        mbar_expect_tx(&full_b[stage], ((p.ablate & 1) ? 1 : 2) * C::B_TILE_BYTES);
+                        tma_load_2d(stage_b_hi(stage), &p.tmBhi, &full_b[stage], kcol, n_tile * BN);
+                        if (!(p.ablate & 1)) tma_load_2d(stage_b_lo(stage), &p.tmBlo, &full_b[stage], kcol, n_tile * BN);
+                    }
                     TL(gp, 1); ++gp;
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -393,11 +452,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     } else if (warp == 1 || warp >= 14) {
         // ============================================================== MMA issuers (warps 1, 14, 15: K-blocks round-robin)
         const uint32_t me = warp == 1 ? 0u : (uint32_t)(warp - 13);
-        if (lane == 0 && me < (uint32_t)C::ISSUERS) {
+        if (lane == 0 && me < (uint32_t)C::ISSUERS && cta_rank == 0) {     // PAIR: the leader CTA issues for both
             // instruction descriptor: D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10) | F16 (0, 0), both K-major, N>>3 at bit 17, M>>4 at bit 24
-            const uint32_t idesc = (1u << 4) | (MODE ? 0u : ((2u << 7) | (2u << 10))) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+            const uint32_t idesc = (1u << 4) | (MODE ? 0u : ((2u << 7) | (2u << 10))) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(((PAIR ? 2 : 1) * TILE_M) >> 4) << 24);
             auto mma = [&](uint32_t d, uint32_t a, uint64_t b, uint32_t acc) {
-                if constexpr (MODE) umma_f16_ts(d, a, b, idesc, acc); else umma_tf32_ts(d, a, b, idesc, acc);
+                if constexpr (PAIR) umma_f16_ts_pair(d, a, b, idesc, acc);
+                else if constexpr (MODE) umma_f16_ts(d, a, b, idesc, acc); else umma_tf32_ts(d, a, b, idesc, acc);
             };
             // Issuing a tcgen05.mma blocks the thread for about its execution time, and every barrier wait costs a few
             // hundred cycles; with a single issuer the tensor pipe idled ~40% of each K-block.  ISSUERS threads take
@@ -407,7 +467,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             int stage = 0; uint32_t phase = 0;
             const uint32_t buf = me;
             const bool a_exact = p.a_exact != 0, single = p.single != 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < tile_end; tile += tile_step) {
                 for (int kb = 0; kb < kblocks; ++kb, ++g) {
                     if (turn == me) {
                         // operands first (normally long complete), the partial-sum buffer last: its release by the drain
@@ -442,8 +502,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             if (k < ksteps) mma(d_tmem, a_hi + 8 * k, b_hi + 2 * k, (k != 0) | !single);
-                        umma_commit(&empty[stage]);                           // smem slot + TMEM A slot reusable once these MMAs retire
-                        umma_commit(&d_full[buf]);                            // partial sum of this K-block complete
+                        if constexpr (PAIR) {                                 // both CTAs' producers / converters / drain warps
+                            umma_commit_pair(&empty[stage]);
+                            umma_commit_pair(&d_full[buf]);
+                        } else {
+                            umma_commit(&empty[stage]);                       // smem slot + TMEM A slot reusable once these MMAs retire
+                            umma_commit(&d_full[buf]);                        // partial sum of this K-block complete
+                        }
                         TL(g, 4);
                         ++mine;
                     }
@@ -459,7 +524,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         const int row = quarter * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
         int stage = 0, land = 0; uint32_t phase = 0, lphase = 0; uint32_t gc = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < tile_end; tile += tile_step) {
             for (int kb = 0; kb < kblocks; ++kb) {
                 const uint32_t dst = tmem_base + C::TMEM_A0 + stage * 64 + lane_addr;
                 if constexpr (MODE == 0) {
@@ -498,7 +563,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                         mbar_wait<true>(&full_a[land], lphase);
                         if (warp == 2 && lane == 0) TL(gc, 5);
                     }
-                    const int m_tile = tile / p.tiles_n, rem = m_tile % tiles_per_img;
+                    const int m_tile = m_tile_of(tile), rem = m_tile % tiles_per_img;
                     const int ho0 = (rem / p.tiles_x) * p.BH, wo0 = (rem % p.tiles_x) * BW;
                     const int ty = row >> p.bw_log2, tx = row & (BW - 1);
                     const int ho = ho0 + ty, wo = wo0 + tx;
@@ -625,7 +690,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&conv[stage]);                     // one arrival per warp
+                if (lane == 0) { if constexpr (PAIR) mbar_arrive_leader(&conv[stage]); else mbar_arrive(&conv[stage]); }   // one arrival per warp
                 if (warp == 2 && lane == 0) TL(gc, 6);
                 ++gc;
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -656,14 +721,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         const bool dma = lane == 0 && quarter < CHUNKS;                       // this thread drives the TMA traffic of chunk `quarter`
         uint32_t g = 0, tile_par = 0;
         uint32_t buf = 0, dpar = 0;                                           // partial-sum buffer of K-block g (g % ISSUERS) and its phase
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, tile_par ^= 1) {
+        for (int tile = tile0; tile < tile_end; tile += tile_step, tile_par ^= 1) {
             // The tensor pipe is stalled at a tile boundary until this tile's first partial sums are drained, so nothing is
             // computed up front: the tile coordinates are decoded after the first K-block's drain.
             int img = 0, ho0 = 0, wo0 = 0, n0 = 0;
             auto out_pixel = [&](int r) -> int {                              // output pixel of this warp's row r, -1 = outside the image
                 const int prow = quarter * 32 + r;
                 const int ho = ho0 + (prow >> p.bw_log2), wo = wo0 + (prow & (BW - 1));
-                return (ho < p.Ho && wo < p.Wo) ? (img * p.Ho + ho) * p.Wo + wo : -1;
+                return (ho < p.Ho && wo < p.Wo && img < p.N) ? (img * p.Ho + ho) * p.Wo + wo : -1;   // (img >= N: the odd tile out of a PAIR)
             };
             // ---- after the first K-block (tiles with a long K loop): decode the tile and fetch the group's folded-BN shift (the
             //      scale is folded into the weights; arrays are padded to cout_pad >= n0 + HALF) - safe to overwrite: every
@@ -697,7 +762,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 }
             };
             auto decode = [&]() {
-                const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
+                const int n_tile = tile % p.tiles_n, m_tile = m_tile_of(tile);
                 img = m_tile / tiles_per_img;
                 const int rem = m_tile - img * tiles_per_img;
                 ho0 = (rem / p.tiles_x) * p.BH; wo0 = (rem % p.tiles_x) * BW;
@@ -707,9 +772,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             if (early) decode();
             if (early_par) fetch_params();
             if (early_res) fetch_residual();
+            // The slab is released by the previous tile's bulk stores (they read it for ~1 500 cycles after being issued).  The
+            // drain warps must not sit in that wait right after the first K-block - the MMA issuers are at most ISSUERS K-blocks
+            // ahead and stall with them - so the wait (+ the group barrier that publishes it, + the residual prefetch into the
+            // slab) moves to the drain of K-block `slab_kb`, by when the stores are long done; without a residual nobody
+            // touches the slab before phase 1 and the wait moves there.
+            const int slab_kb = (p.ablate & 128) ? 0 : (kblocks > 2 ? 2 : kblocks - 1);
             auto after_first_kblock = [&]() {
                 if (!early) decode();
                 if (!early_par) fetch_params();
+            };
+            auto slab_ready = [&]() {
                 if (dma) bulk_wait_read();
                 group_sync();
                 if (!early_res) fetch_residual();
@@ -725,7 +798,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     for (int it = 0; it < 32 / RR; ++it) {
                         const int row = it * RR + rrow, prow = quarter * 32 + row;
                         const int ho = ho0 + (prow >> p.bw_log2), wo = wo0 + (prow & (BW - 1));
-                        if (ho >= p.Ho || wo >= p.Wo || n0 + pc * 4 + 3 >= p.Cout) continue;
+                        if (ho >= p.Ho || wo >= p.Wo || img >= p.N || n0 + pc * 4 + 3 >= p.Cout) continue;
                         int rp = (img * p.Ho + ho) * p.Wo + wo;
                         if (r_resize) {
                             const int hs = min((int)floorf(ho * rs_y), p.res2_h - 1), ws = min((int)floorf(wo * rs_x), p.res2_w - 1);
@@ -781,7 +854,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                             else {
                                 tc_fence_before();
                                 __syncwarp();
-                                if (lane == 0) mbar_arrive(&d_empty[buf]);
+                                if (lane == 0) { if constexpr (PAIR) mbar_arrive_leader(&d_empty[buf]); else mbar_arrive(&d_empty[buf]); }
                             }
 #pragma unroll
                             for (int j = 0; j < 16; ++j) accum(acc[(pc + 1) * 16 + j], vb[j]);
@@ -793,8 +866,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 if (++buf == (uint32_t)C::ISSUERS) { buf = 0; dpar ^= 1; }
                 if (kb == 0) after_first_kblock();
                 else if (kb == 1) add_shift();                                // off the tile-boundary critical path
+                if (kb == slab_kb && (has_res || (p.ablate & 128))) slab_ready();
             }
             if (kblocks == 1) add_shift();
+            if (!has_res && !(p.ablate & 128)) slab_ready();
             // ---- fused epilogue (pixel per thread == TMEM lane, in place in the slab):
             //      y = post_scale * act(acc [+ res1]) [+ res2]      (acc already = conv*scale + shift)
             asm volatile("cp.async.wait_all;" ::: "memory");                  // params (+ this warp's rows of a cp.async residual)
@@ -901,7 +976,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if constexpr (PAIR) {
+        cluster_sync_all();                                              // no remote signal may target a CTA that has exited
+        if (warp == 1) tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
+    } else if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
 // ----------------------------------------------------------------------------------------------- host side
@@ -927,6 +1005,36 @@ bool make_map(CUtensorMap* map, void* base, int rank, const cuuint64_t* dims, co
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     return fn(map, dtype, rank, base, dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
               swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN, int MODE>
+int launch_pair(fcp_ctx* ctx, const TcParams& p) {
+    using C = Cfg<BN, MODE>;
+    static uint64_t configured = 0;
+    if (!((configured >> (ctx->device & 63)) & 1)) {
+        FCP_CUDA(ctx, (cudaFuncSetAttribute(conv_tc_kernel<BN, MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES)));
+        configured |= (uint64_t)1 << (ctx->device & 63);
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    // persistent kernel: exactly as many pairs as can be resident at once (GPCs with an odd SM count leave an SM unpaired)
+    static int resident[64] = {0};
+    if (!resident[ctx->device & 63]) {
+        cfg.gridDim = dim3(2 * (ctx->sm_count / 2));
+        int n = 0;
+        FCP_CUDA(ctx, (cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<BN, MODE, 1>, &cfg)));
+        resident[ctx->device & 63] = std::max(1, std::min(n, ctx->sm_count / 2));
+        if (getenv("FCP_LOG_CONV")) fprintf(stderr, "[conv_tc] %d CTA pairs resident on %d SMs\n", n, ctx->sm_count);
+    }
+    const int pairs = std::min(p.pair_tiles, resident[ctx->device & 63]);
+    cfg.gridDim = dim3(2 * pairs);
+    FCP_CUDA(ctx, (cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, MODE, 1>, p)));
+    FCP_KERNEL_CHECK(ctx);
+    return FCP_OK;
 }
 
 template <int BN, int MODE>
@@ -1035,7 +1143,14 @@ int launch_conv_tc(fcp_ctx* ctx, const ConvOp& op) {
     const cuuint64_t K = f16 ? ((cuuint64_t)p.KH * p.KW * p.cin_p + 63) / 64 * 64 : (cuuint64_t)p.KH * p.KW * p.cin_p;
     cuuint64_t bdims[2] = {K, (cuuint64_t)wt.cout_pad};
     cuuint64_t bstr[1] = {K * (f16 ? 2 : 4)};
-    cuuint32_t bbox[2] = {(cuuint32_t)(f16 ? 64 : 32), (cuuint32_t)BN};
+    // CTA pairs (cta_group::2): opt-in, measured SLOWER than one CTA per tile - FCP_TC_PAIR=1 takes the wide
+    // f16 tiles of launches that give every pair work, FCP_TC_PAIR=2 every wide f16 tile (tests)
+    const char* pair_s = getenv("FCP_TC_PAIR");
+    const int pair_env = pair_s ? atoi(pair_s) : 0;
+    const int m_tiles = p.N * p.tiles_x * p.tiles_y;
+    p.pair_tiles = p.tiles_n * ((m_tiles + 1) / 2);
+    const bool pair = pair_env && f16 && !stem && BN == 128 && (p.pair_tiles >= ctx->sm_count / 2 || pair_env > 1);
+    cuuint32_t bbox[2] = {(cuuint32_t)(f16 ? 64 : 32), (cuuint32_t)(pair ? BN / 2 : BN)};
     const CUtensorMapDataType bt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     if (!make_map(&p.tmBhi, f16 ? wt.h_hi : (void*)wt.w_hi, 2, bdims, bstr, bbox, bt) ||
         !make_map(&p.tmBlo, f16 ? wt.h_lo : (void*)wt.w_lo, 2, bdims, bstr, bbox, bt))
@@ -1069,6 +1184,7 @@ int launch_conv_tc(fcp_ctx* ctx, const ConvOp& op) {
     p.ablate = ablate;
     auto do_launch = [&]() -> int {
         if (f16) {
+            if (pair) return launch_pair<128, 1>(ctx, p);
             if (BN == 128) return launch<128, 1>(ctx, p);
             if (BN == 64) return launch<64, 1>(ctx, p);
             return launch<32, 1>(ctx, p);

@@ -130,6 +130,25 @@ def test_conv2d_fast_mode_accuracy_class(ctx):
     assert err[3] > 20 * err[2]
 
 
+def test_conv2d_cta_pair_variant_matches(ctx):
+    """Opt-in cta_group::2 variant of the wide f16 tiles (FCP_TC_PAIR; measured slower, kept as a measured experiment):
+    two CTAs of a cluster share one 256-row MMA and half a weight tile each.  Same results as one CTA per tile, bit for
+    bit (the arithmetic per output element is identical), also with an odd number of pixel tiles (phantom tile)."""
+    import os
+    g = torch.Generator().manual_seed(21)
+    for (n, h, w, cin, cout, k, pad) in [(3, 17, 15, 128, 256, 3, 1), (2, 32, 32, 256, 128, 1, 0)]:
+        x = torch.randn((n, h, w, cin), generator=g).numpy()
+        wt = (torch.randn((cout, cin, k, k), generator=g) * (2.0 / (cin * k * k)) ** 0.5).numpy()
+        res = torch.randn((n, h, w, cout), generator=g).numpy()
+        one = ctx.conv2d(x, wt, 1, pad, None, None, res, "relu", 0.0, 2)
+        os.environ["FCP_TC_PAIR"] = "2"
+        try:
+            two = ctx.conv2d(x, wt, 1, pad, None, None, res, "relu", 0.0, 2)
+        finally:
+            del os.environ["FCP_TC_PAIR"]
+        assert np.array_equal(one, two)
+
+
 def test_conv2d_f16x3_dynamic_range(ctx):
     """The block scaling of the 3xFP16 mode: pixel rows spanning 2^-40 .. 2^40 (far outside fp16's 2^-24 .. 2^16), output
     channels whose weights span 2^-12 .. 1, exact zeros, and rows of zeros.  Error is measured per output element against
