@@ -75,7 +75,7 @@ def _shapes(log):
 
 def _bn(cout):
     cp = (cout + 31) // 32 * 32
-    return 128 if cp % 128 == 0 else (64 if cp % 64 == 0 else 32)
+    return 128 if cp % 128 == 0 or cp == 96 else (64 if cp % 64 == 0 else 32)
 
 
 def launches2(src, shapes_log, dst, traffic_json=None):
