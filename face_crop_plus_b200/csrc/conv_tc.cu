@@ -291,8 +291,9 @@ template <int BN, int MODE> struct Cfg {
     static constexpr int HALVES = MODE ? 2 : 1;                           // 32-channel fp32 landing units (TMA boxes) per K-block
     static constexpr int B_TILE_BYTES = BN * 128;                         // BN rows x (32 tf32 | 64 fp16)
     static constexpr int B_SLOT_BYTES = 2 * B_TILE_BYTES;                 // w_hi + w_lo of one K-block
-    // The K loop is bound by the latency of one trip round the pipeline (TMA issue + landing + convert + MMA issue +
-    // retire ~ 3300 cycles, measured) divided by its depth, not by any bandwidth.  The fp32 A tile only lives from its
+    // One trip round the pipeline (TMA issue + landing + convert + MMA issue + retire) takes ~3300 cycles (measured), so
+    // its depth sets the K-block period until the co-limiters of DESIGN.md 5.3 take over (TMA ingest of 64 KiB per K-block
+    // at ~42 B/cycle/SM, ~1200 busy converter cycles, 144 KiB through the shared-memory port).  The fp32 A tile only lives from its
     // landing to its conversion, so it gets its own short ring (LANDINGS units of 16 KiB); a pipeline STAGE is a weight
     // slot in shared memory plus an (a_hi | a_lo) slot in tensor memory, both held until the K-block's MMAs retire.
     static constexpr int STAGES = MODE ? (BN >= 128 ? 3 : (BN == 64 ? 4 : 6)) : (BN >= 128 ? 4 : (BN == 64 ? 5 : 6));

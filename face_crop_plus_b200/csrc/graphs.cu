@@ -447,7 +447,8 @@ static int rrdbnet_forward(Exec& ex, const std::function<int(Tensor)>& fill_firs
     // finalize_rrdbnet) - every x_j tile is read by ONE or two launches instead of by each of the 5 - j later convs, the
     // partial sums of the not-yet-final convs accumulate in place in the slab (fp32, residual path of the conv epilogue).
     // FCP_RRDB_LAYERWISE=1 keeps the conv-by-conv schedule (also the schedule of the 3xTF32 and CUDA-core routes).
-    const bool source_major = ex.ctx->use_tc >= 2 && !getenv("FCP_RRDB_LAYERWISE");
+    const bool source_major = ex.ctx->use_tc >= 2 && !getenv("FCP_RRDB_LAYERWISE") &&
+                              (size_t)h * w >= 64;        // smaller maps run on the CUDA-core kernel (conv_tc_supported)
     const int SC = source_major ? 256 : 192;
     Tensor slab[3];
     for (auto& s : slab) s = ex.alloc(nb, h, w, SC);

@@ -60,6 +60,15 @@ def test_enhance_source_major_schedule_vs_layerwise_and_fp32(ctx):
     print(f"source-major vs layerwise {e1:.3e}, vs CUDA-core fp32 {e2:.3e} (|y| max {np.abs(fp32).max():.3f})")
     assert np.isfinite(got).all() and e1 < 1e-4 and e2 < 1e-4
     assert not np.array_equal(got, layerwise)          # the switch really selects another schedule
+    # maps under 64 pixels stay on the CUDA-core kernel and therefore on the conv-by-conv schedule: must still run
+    tiny = torch.from_numpy(synth.make_images(1, 7, 6, seed=6)).permute(0, 3, 1, 2).float().contiguous().numpy() / 255
+    t2 = ctx.enhance_forward(tiny)
+    ctx.set_conv_impl(0)
+    try:
+        t0 = ctx.enhance_forward(tiny)
+    finally:
+        ctx.set_conv_impl(2)
+    assert t2.shape == (1, 3, 28, 24) and float(np.abs(t2 - t0).max()) < 1e-4
 
 
 def test_enhance_u8_batched_equals_per_image_and_f32_path(ctx):
