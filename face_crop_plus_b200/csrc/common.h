@@ -218,6 +218,7 @@ int launch_stem_rows(fcp_ctx* ctx, const void* src, int mode, int n, int h, int 
 int launch_conv3_first(fcp_ctx* ctx, const float* src_nchw, float in_scale, int n, int h, int w, const float* w_kn,
                        const float* shift, Tensor out);
 // same, input = u8 NHWC RGB (the value / 255, like rrdb.py:142 on a 0..255 float image)
+int launch_conv3_last(fcp_ctx* ctx, Tensor in, const float* packed, Tensor out);
 int launch_conv3_first_u8(fcp_ctx* ctx, const uint8_t* src_nhwc, int n, int h, int w, const float* w_kn, const float* shift, Tensor out);
 int launch_maxpool3s2(fcp_ctx* ctx, Tensor in, Tensor out);
 int launch_global_avgpool(fcp_ctx* ctx, Tensor in, float* out_nc);                     // out[n][c] = mean_hw

@@ -377,6 +377,21 @@ int finalize_rrdbnet(fcp_ctx* ctx) {
                 FCP_TRY(pack_conv(ctx, m, {p}, "", p));
             }
     for (const char* c : {"trunk_conv", "upconv1", "upconv2", "HRconv", "conv_last"}) FCP_TRY(pack_conv(ctx, m, {c}, "", c));
+    // ---- conv_last (64 -> 3) for the direct fp32 kernel (misc.cu conv3_last_kernel): [tap][cin][cout] + bias
+    {
+        auto iw = m.host.find("conv_last.weight");
+        auto ib = m.host.find("conv_last.bias");
+        if (iw != m.host.end() && iw->second.shape.size() == 4 && iw->second.shape[0] == 3 && iw->second.shape[1] == 64 &&
+            iw->second.shape[2] == 3 && iw->second.shape[3] == 3) {
+            std::vector<float> pk(9 * 64 * 3 + 4, 0.f);
+            for (int o = 0; o < 3; ++o)
+                for (int c = 0; c < 64; ++c)
+                    for (int t = 0; t < 9; ++t) pk[(t * 64 + c) * 3 + o] = iw->second.data[((size_t)o * 64 + c) * 9 + t];
+            if (ib != m.host.end())
+                for (int o = 0; o < 3; ++o) pk[9 * 64 * 3 + o] = ib->second.data[o];
+            m.vec["conv_last.direct"] = pk;
+        }
+    }
     // ---- source-major packing of the dense blocks (rrdbnet_forward, tensor-core route).  ResidualDenseBlock_5C
     // (_layers.py:179-186) is conv_k([x, x1 .. x_{k-1}]) for k = 1..5: conv_k's weight splits by input channel range into one
     // block per SOURCE x_j, and one pass per source computes that source's contribution to every later conv at once.
@@ -521,7 +536,12 @@ static int rrdbnet_forward(Exec& ex, const std::function<int(Tensor)>& fill_firs
     ex.conv("HRconv", u2, hr, 1, 1, FCP_ACT_LRELU, lre);
     ex.free(u2);
     x4 = ex.alloc(nb, 4 * h, 4 * w, 3, 4);
-    ex.conv("conv_last", hr, x4, 1, 1, FCP_ACT_NONE);
+    auto direct = ex.model->vec.find("conv_last.direct");
+    if (ex.ctx->use_tc >= 1 && direct != ex.model->vec.end() && !getenv("FCP_CONV_LAST_GEMM")) {
+        if (ex.ok() && !ex.dry) ex.status = launch_conv3_last(ex.ctx, hr, direct->second.data(), x4);   // 3 output channels: direct fp32 conv
+    } else {
+        ex.conv("conv_last", hr, x4, 1, 1, FCP_ACT_NONE);
+    }
     ex.free(hr);
     return ex.status;
 }

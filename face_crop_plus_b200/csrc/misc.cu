@@ -185,6 +185,59 @@ __global__ void __launch_bounds__(256) conv3_first_kernel(const void* __restrict
         *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
 }
 
+// ------------------------------------------------------------------------------- RRDB conv_last (3x3, 64 -> 3)
+// rrdb.py:81 conv_last at the x4 resolution: 3 output channels, so an implicit GEMM would read every input tile for three
+// columns of MMA (3.5 ms per 8.4 M pixels on the tensor-core kernel).  Direct fp32 convolution instead: a block stages the
+// (8+2) x (32+2) halo of its 8 x 32 output pixels in shared memory (pixel pitch 68 floats: conflict-free float4 reads), one
+// thread per pixel, the 1728 weights are FFMA constant-bank operands (no load instructions for them).
+__constant__ float c_last_w[9 * 64 * 3];   // [tap][cin][cout]
+__constant__ float c_last_b[4];
+constexpr int CL_TW = 32, CL_TH = 8, CL_PITCH = 68;
+constexpr int CL_SMEM = (CL_TH + 2) * (CL_TW + 2) * CL_PITCH * 4;
+
+__global__ void __launch_bounds__(256) conv3_last_kernel(const float* __restrict__ in, int in_cs, int in_co, int H, int W,
+                                                         float* __restrict__ out, int out_cs, int out_co) {
+    extern __shared__ __align__(16) float cl_tile[];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int w0 = blockIdx.x * CL_TW, h0 = blockIdx.y * CL_TH, n = blockIdx.z;
+    constexpr int TOTAL = (CL_TH + 2) * (CL_TW + 2) * 16, BATCH = 8;        // 16-byte pieces of the halo; loads in flight per thread
+    for (int base = threadIdx.x; base < TOTAL; base += 256 * BATCH) {
+        float4 v[BATCH];
+#pragma unroll
+        for (int k = 0; k < BATCH; ++k) {
+            const int i = base + k * 256, px = i >> 4, q = i & 15;
+            const int hi = h0 + px / (CL_TW + 2) - 1, wi = w0 + px % (CL_TW + 2) - 1;
+            v[k] = make_float4(0.f, 0.f, 0.f, 0.f);                        // zero padding
+            if (i < TOTAL && hi >= 0 && hi < H && wi >= 0 && wi < W)
+                v[k] = __ldg(reinterpret_cast<const float4*>(in + (((size_t)n * H + hi) * W + wi) * in_cs + in_co + q * 4));
+        }
+#pragma unroll
+        for (int k = 0; k < BATCH; ++k) {
+            const int i = base + k * 256;
+            if (i < TOTAL) *reinterpret_cast<float4*>(cl_tile + (i >> 4) * CL_PITCH + (i & 15) * 4) = v[k];
+        }
+    }
+    __syncthreads();
+    const int ho = h0 + ty, wo = w0 + tx;
+    if (ho >= H || wo >= W) return;
+    float a0 = c_last_b[0], a1 = c_last_b[1], a2 = c_last_b[2];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const float* px = cl_tile + ((ty + t / 3) * (CL_TW + 2) + tx + t % 3) * CL_PITCH;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const float4 x = *reinterpret_cast<const float4*>(px + q * 4);
+            const float* w = c_last_w + (t * 64 + q * 4) * 3;
+            a0 = fmaf(x.x, w[0], a0); a1 = fmaf(x.x, w[1], a1); a2 = fmaf(x.x, w[2], a2);
+            a0 = fmaf(x.y, w[3], a0); a1 = fmaf(x.y, w[4], a1); a2 = fmaf(x.y, w[5], a2);
+            a0 = fmaf(x.z, w[6], a0); a1 = fmaf(x.z, w[7], a1); a2 = fmaf(x.z, w[8], a2);
+            a0 = fmaf(x.w, w[9], a0); a1 = fmaf(x.w, w[10], a1); a2 = fmaf(x.w, w[11], a2);
+        }
+    }
+    float* dst = out + (((size_t)n * H + ho) * W + wo) * out_cs + out_co;
+    dst[0] = a0; dst[1] = a1; dst[2] = a2;
+}
+
 // ------------------------------------------------------------------------------------------- maxpool 3x3/s2/p1
 __global__ void maxpool3s2_kernel(const float* __restrict__ in, int N, int H, int W, int C, int in_cs, int in_co,
                                   float* __restrict__ out, int Ho, int Wo, int out_cs, int out_co) {
@@ -371,6 +424,23 @@ int launch_conv3_first_u8(fcp_ctx* ctx, const uint8_t* src_nhwc, int n, int h, i
     size_t total = (size_t)n * h * w;
     conv3_first_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(src_nhwc, 255.f, n, h, w, w_kn, shift,
                                                                                        out.p, out.cs, out.co);
+    FCP_KERNEL_CHECK(ctx);
+    return FCP_OK;
+}
+
+// `packed` = host [9*64*3 weights (tap, cin, cout)] + [3 bias, 1 pad] (finalize_rrdbnet); re-uploaded per launch, stream-ordered,
+// because the constant bank is per device and several contexts may hold different weights
+int launch_conv3_last(fcp_ctx* ctx, Tensor in, const float* packed, Tensor out) {
+    if (in.c != 64 || out.c != 3 || ((in.cs | in.co) & 3)) return fail(ctx, FCP_ERR_INVALID, "conv3_last: expects a 64 -> 3 convolution");
+    static uint64_t configured = 0;                    // one bit per device: the attribute is per device
+    if (!((configured >> (ctx->device & 63)) & 1)) {
+        FCP_CUDA(ctx, cudaFuncSetAttribute(conv3_last_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CL_SMEM));
+        configured |= (uint64_t)1 << (ctx->device & 63);
+    }
+    FCP_CUDA(ctx, cudaMemcpyToSymbolAsync(c_last_w, packed, sizeof(float) * 9 * 64 * 3, 0, cudaMemcpyHostToDevice, ctx->stream));
+    FCP_CUDA(ctx, cudaMemcpyToSymbolAsync(c_last_b, packed + 9 * 64 * 3, sizeof(float) * 4, 0, cudaMemcpyHostToDevice, ctx->stream));
+    dim3 grid((in.w + CL_TW - 1) / CL_TW, (in.h + CL_TH - 1) / CL_TH, in.n);
+    conv3_last_kernel<<<grid, 256, CL_SMEM, ctx->stream>>>(in.p, in.cs, in.co, in.h, in.w, out.p, out.cs, out.co);
     FCP_KERNEL_CHECK(ctx);
     return FCP_OK;
 }
