@@ -57,6 +57,7 @@ struct ConvOp {
     int up_in = 0;             // read the input through a nearest x2 upsample (logical size = 2x physical)
     int act = FCP_ACT_NONE;
     float slope = 0.f;
+    int out_add = 0;           // out += result instead of out = result (tensor-core kernel with the TMA epilogue only; RRDB skip, graphs.cu)
     int act_cols = 1 << 30;    // the activation applies to output channels < act_cols only (tcgen05 kernel; RRDBNet source-major passes)
     const float* res1 = nullptr; int res1_cs = 0, res1_co = 0;              // added before the activation
     float post_scale = 1.f;

@@ -78,6 +78,7 @@ struct alignas(64) TcParams {
     // means and write exact fp16 integers into tensor memory.  K-block b = tap rows 2b, 2b+1 (32 K slots each, 21 used).
     CUtensorMap tmStem;
     int stem, stem_H, stem_W, stem_box_w, stem_box_h;
+    int out_add;                               // TMA epilogue: the result is ADDED to the output tensor (cp.reduce.async.bulk .add)
     int act_cols;                              // channels >= act_cols skip the activation (general epilogue form only)
     int single;                                // opt-in fast mode: hi x hi only (one pass, 11 significant bits per operand)
     int a_exact;                               // the activations are exactly representable in 11 significant bits (u8 - mean):
@@ -142,6 +143,11 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
 // smem (128B-swizzled box) -> global tensor; completion tracked by the issuing thread's bulk async-group
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src_smem, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+// ... the same box ADDED to the tensor (fp32 add performed in L2): out += slab
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, uint32_t src_smem, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                  ::"l"(map), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -932,7 +938,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 group_sync();                                                 // all 128 pixel rows of the group's chunks are final
                 if (warp == 6 && lane == 0) TL(g - 1, 12);
                 if (dma && !(p.ablate & 2)) {
-                    if (n0 + quarter * 32 < p.Cout) tma_store_4d(&p.tmOut, S + quarter * C::CHUNK_BYTES, n0 + quarter * 32, wo0, ho0, img);
+                    if (n0 + quarter * 32 < p.Cout) {
+                        if (p.out_add) tma_reduce_add_4d(&p.tmOut, S + quarter * C::CHUNK_BYTES, n0 + quarter * 32, wo0, ho0, img);
+                        else tma_store_4d(&p.tmOut, S + quarter * C::CHUNK_BYTES, n0 + quarter * 32, wo0, ho0, img);
+                    }
                     bulk_commit();
                 }
             } else {
@@ -1141,6 +1150,7 @@ int launch_conv_tc(fcp_ctx* ctx, const ConvOp& op) {
     p.a_exact = op.a_exact || stem;
     p.single = op.impl == 3;
     p.act_cols = op.act_cols;
+    p.out_add = op.out_add;
     const cuuint64_t K = f16 ? ((cuuint64_t)p.KH * p.KW * p.cin_p + 63) / 64 * 64 : (cuuint64_t)p.KH * p.KW * p.cin_p;
     cuuint64_t bdims[2] = {K, (cuuint64_t)wt.cout_pad};
     cuuint64_t bstr[1] = {K * (f16 ? 2 : 4)};
@@ -1169,6 +1179,7 @@ int launch_conv_tc(fcp_ctx* ctx, const ConvOp& op) {
         p.out_tma = !op.res3 && tensor_ok(op.out.p + op.out.co, op.out.cs) && getenv("FCP_TC_NO_TMA_EPI") == nullptr;
         if (p.out_tma && !epi_map(&p.tmOut, op.out.p + op.out.co, op.out.cs))
             return fail(ctx, FCP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the output tensor");
+        if (op.out_add && !p.out_tma) return fail(ctx, FCP_ERR_INVALID, "conv_tc: out_add needs the TMA epilogue");
         const float* rsrc = op.res1 ? op.res1 : op.res2;
         const int r_cs = op.res1 ? op.res1_cs : op.res2_cs, r_co = op.res1 ? op.res1_co : op.res2_co;
         p.res_tma = rsrc && !(op.res2 && op.res2_h) && tensor_ok(rsrc + r_co, r_cs) && getenv("FCP_TC_NO_TMA_EPI") == nullptr;

@@ -473,8 +473,10 @@ static int rrdbnet_forward(Exec& ex, const std::function<int(Tensor)>& fill_firs
                         ? FCP_OK : fail(ex.ctx, FCP_ERR_CUDA, "slab init copy failed");
     int cur = 0;
     for (int i = 0; i < ex.model->rrdb_blocks && ex.ok(); ++i) {
+        // source-major: the third dense block ADDS 0.2 * its output onto the RRDB input where it lies (slab[cur].x, TMA
+        // reduce-add store) - no second residual in the epilogue, and the next RRDB starts from the same slab
         const int order_in[3] = {cur, (cur + 1) % 3, (cur + 2) % 3};
-        const int order_out[3] = {(cur + 1) % 3, (cur + 2) % 3, (cur + 1) % 3};
+        const int order_out[3] = {(cur + 1) % 3, (cur + 2) % 3, source_major ? cur : (cur + 1) % 3};
         for (int r = 0; r < 3; ++r) {
             std::string p = "RRDB_trunk." + std::to_string(i) + ".RDB" + std::to_string(r + 1);
             Tensor S = slab[order_in[r]], T = slab[order_out[r]];
@@ -496,8 +498,8 @@ static int rrdbnet_forward(Exec& ex, const std::function<int(Tensor)>& fill_firs
                 ex.conv(p + ".s3", S.slice(128, 32), S.slice(160, 96), 1, 1, FCP_ACT_LRELU, acc_into(S.slice(160, 96), true, 32));
                 ConvOp e = acc_into(S.slice(192, 64), true, 1 << 30);                      // next x = c5 + 0.2 * W5[:, x4] x4
                 if (r == 2) {                                                         // RRDB: out * 0.2 + x   (_layers.py:200)
-                    e.post_scale2 = 0.2f;
-                    e.res3 = slab[cur].p; e.res3_cs = SC; e.res3_co = 0;
+                    e.post_scale = 0.2f;                                              // T.x (= the RRDB input) += 0.2 * (c5 + W5[:, x4] x4)
+                    e.out_add = 1;
                 }
                 ex.conv(p + ".s4", S.slice(160, 32), T.slice(0, 64), 1, 1, FCP_ACT_NONE, e);
                 continue;
@@ -516,7 +518,7 @@ static int rrdbnet_forward(Exec& ex, const std::function<int(Tensor)>& fill_firs
             }
             ex.conv(p + ".conv5", S, T.slice(0, 64), 1, 1, FCP_ACT_NONE, e);
         }
-        cur = (cur + 1) % 3;
+        if (!source_major) cur = (cur + 1) % 3;
     }
     Tensor fea = ex.alloc(nb, h, w, 64);
     ex.conv("trunk_conv", slab[cur].slice(0, 64), fea, 1, 1, FCP_ACT_NONE, with_res1(first));   // first + trunk_conv(..)
