@@ -54,6 +54,8 @@ struct ConvOp {
     const ConvWeights* wt = nullptr;
     int stride = 1, pad = 0;
     int stride_w = 0, pad_w = -1;   // horizontal stride / padding when they differ from the vertical ones (0 / -1: same)
+    Tensor in2; int in2_stride = 1;   // 1x1 stride-1 convs on the tensor-core kernel: second K source - channels [in.c, in.c + in2.c) of the
+                               // weight read `in2` at pixel (ho * in2_stride, wo * in2_stride) (a bottleneck's shortcut conv folded into conv3)
     int up_in = 0;             // read the input through a nearest x2 upsample (logical size = 2x physical)
     int act = FCP_ACT_NONE;
     float slope = 0.f;

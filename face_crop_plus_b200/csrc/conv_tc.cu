@@ -78,6 +78,7 @@ struct alignas(64) TcParams {
     // means and write exact fp16 integers into tensor memory.  K-block b = tap rows 2b, 2b+1 (32 K slots each, 21 used).
     CUtensorMap tmStem;
     int stem, stem_H, stem_W, stem_box_w, stem_box_h;
+    int src2_units;                            // != 0: 32-channel units >= src2_units come from the second source (tmA[1], 1x1 stride-1 convs)
     int out_add;                               // TMA epilogue: the result is ADDED to the output tensor (cp.reduce.async.bulk .add)
     int act_cols;                              // channels >= act_cols skip the activation (general epilogue form only)
     int single;                                // opt-in fast mode: hi x hi only (one pass, 11 significant bits per operand)
@@ -435,7 +436,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                             mbar_wait<true>(&a_free[land], lphase ^ 1);
                             if (hf == 0) TL(gp, 0);
                             mbar_expect_tx(&full_a[land], A_TILE_BYTES);
-                            tma_load_4d(landing(land), &p.tmA[map], &full_a[land], ch * 32, wo0 + dx, ho0 + dy, img);
+                            const CUtensorMap* am = &p.tmA[map];
+                            int chc = ch * 32;
+                            if (p.src2_units && ch >= p.src2_units) { am = &p.tmA[1]; chc -= p.src2_units * 32; }   // folded shortcut conv
+                            tma_load_4d(landing(land), am, &full_a[land], chc, wo0 + dx, ho0 + dy, img);
                             if (++land == C::LANDINGS) { land = 0; lphase ^= 1; }
                         }
                         if (++ch == upt) { ch = 0; ++tap; if (++sx == p.KW) { sx = 0; ++r; } }
@@ -1072,6 +1076,9 @@ bool conv_tc_supported(const ConvOp& op) {
     const ConvWeights& wt = *op.wt;
     if (op.stem_src) return op.impl >= 2 && wt.h_hi && wt.cout_pad == 64 && conv_tc_stem_supported(op.stem_src, op.stem_h, op.stem_w);
     if (wt.cin % KB != 0 || op.up_in) return false;
+    if (op.in2.p && (wt.k != 1 || wt.kh || op.stride != 1 || op.stride_w > 1 || op.in.c % KB != 0 || op.in.c + op.in2.c != wt.cin ||
+                     ((op.in2.cs | op.in2.co) & 3) || (op.in2_stride != 1 && op.in2_stride != 2)))
+        return false;
     const int stride_w = op.stride_w ? op.stride_w : op.stride;
     if ((op.stride != 1 && op.stride != 2) || (stride_w != 1 && stride_w != 2)) return false;
     if (op.stride == 2 && !(wt.k == 1 || wt.k == 3 || wt.kh)) return false;
@@ -1088,7 +1095,7 @@ int launch_conv_tc(fcp_ctx* ctx, const ConvOp& op) {
     const ConvWeights& wt = *op.wt;
     if (!conv_tc_supported(op)) return fail(ctx, FCP_ERR_INVALID, "conv_tc: unsupported shape");
     const bool stem = op.stem_src != nullptr;
-    if (!stem && (op.in.c != wt.cin || op.out.c != wt.cout)) return fail(ctx, FCP_ERR_INVALID, "conv: channel mismatch");
+    if (!stem && (op.in.c + (op.in2.p ? op.in2.c : 0) != wt.cin || op.out.c != wt.cout)) return fail(ctx, FCP_ERR_INVALID, "conv: channel mismatch");
     TcParams p{};
     const int H = stem ? op.stem_h : op.in.h, W = stem ? op.stem_w : op.in.w, cs = op.in.cs;
     p.N = op.out.n; p.Ho = op.out.h; p.Wo = op.out.w; p.Cout = wt.cout; p.Cin = wt.cin;
@@ -1136,13 +1143,23 @@ int launch_conv_tc(fcp_ctx* ctx, const ConvOp& op) {
     for (int py = 0; py < p.stride; ++py)
         for (int px = 0; px < p.stride_w; ++px) {
             const int sh = p.stride, sw = p.stride_w;
-            cuuint64_t dims[4] = {(cuuint64_t)wt.cin, (cuuint64_t)((W - px + sw - 1) / sw), (cuuint64_t)((H - py + sh - 1) / sh), (cuuint64_t)p.N};
+            cuuint64_t dims[4] = {(cuuint64_t)op.in.c, (cuuint64_t)((W - px + sw - 1) / sw), (cuuint64_t)((H - py + sh - 1) / sh), (cuuint64_t)p.N};
             cuuint64_t strides[3] = {(cuuint64_t)sw * cs * 4, (cuuint64_t)sh * W * cs * 4, (cuuint64_t)H * W * cs * 4};
             cuuint32_t box[4] = {KB, (cuuint32_t)BW, (cuuint32_t)BH, 1};
             if (dims[1] == 0 || dims[2] == 0) { dims[1] = dims[1] ? dims[1] : 1; dims[2] = dims[2] ? dims[2] : 1; }
             if (!make_map(&p.tmA[py * 2 + px], base + ((size_t)py * W + px) * cs, 4, dims, strides, box))
                 return fail(ctx, FCP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the activation tensor");
         }
+    if (!stem && op.in2.p) {   // second K source: the (0, 0) sampling of in2 at the output resolution
+        const int s2 = op.in2_stride, H2 = op.in2.h, W2 = op.in2.w, cs2 = op.in2.cs;
+        if ((H2 + s2 - 1) / s2 != p.Ho || (W2 + s2 - 1) / s2 != p.Wo || op.in2.n != p.N) return fail(ctx, FCP_ERR_INVALID, "conv_tc: second source does not match the output grid");
+        cuuint64_t dims[4] = {(cuuint64_t)op.in2.c, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)p.N};
+        cuuint64_t strides[3] = {(cuuint64_t)s2 * cs2 * 4, (cuuint64_t)s2 * W2 * cs2 * 4, (cuuint64_t)H2 * W2 * cs2 * 4};
+        cuuint32_t box[4] = {KB, (cuuint32_t)BW, (cuuint32_t)BH, 1};
+        if (!make_map(&p.tmA[1], op.in2.p + op.in2.co, 4, dims, strides, box))
+            return fail(ctx, FCP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the second activation tensor");
+        p.src2_units = op.in.c / 32;
+    }
     const bool f16 = op.impl >= 2;
     if (f16 && !wt.h_hi) return fail(ctx, FCP_ERR_INVALID, "conv_tc: this convolution has no fp16 packing");
     p.cin_p = f16 ? wt.cin_p : wt.cin;

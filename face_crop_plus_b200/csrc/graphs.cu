@@ -125,43 +125,44 @@ int finalize_retinaface(fcp_ctx* ctx) {
                 FCP_TRY(pack_conv(ctx, m, {p + ".conv" + std::to_string(c)}, p + ".bn" + std::to_string(c), p + ".conv" + std::to_string(c)));
             if (b == 0) FCP_TRY(pack_conv(ctx, m, {p + ".downsample.0"}, p + ".downsample.1", p + ".downsample"));
         }
-    // layer1.0: conv3 (64 -> 256 on the block's 3x3 output) and the shortcut's downsample conv (64 -> 256 on the block
-    // input, stride 1) see the same pixels, so relu(bn3(conv3(h)) + bn_d(conv_d(x))) is ONE 1x1 conv over the channel
-    // concatenation [h | x] with the folded weights side by side and the folded shifts added: the 256-channel shortcut
-    // tensor (268 MB per 64 images at 1024^2) is neither written nor read back (retinaface_forward, tensor-core routes).
-    {
-        const std::string p = "body.layer1.0";
-        auto fold = [&](const std::string& conv, const std::string& bn, std::vector<float>& w, std::vector<float>& beta) -> bool {
+    // block 0 of every layer: relu(bn3(conv3(h)) + bn_d(conv_d(x))) is ONE 1x1 conv over the K concatenation [h | x(sampled at
+    // the block's stride)], folded weights side by side, folded shifts added (tensor-core routes, `bottleneck`): the shortcut
+    // tensor (4 x planes channels at the output resolution; 268 MB per 64 images in layer1) is neither written nor read back.
+    for (int li = 1; li <= 4; ++li) {
+        const std::string p = "body.layer" + std::to_string(li) + ".0";
+        const int cout = 256 << (li - 1), cin3 = 64 << (li - 1), cind = li == 1 ? 64 : 128 << (li - 1);
+        auto fold = [&](const std::string& conv, const std::string& bn, int cin, std::vector<float>& w, std::vector<float>& beta) -> bool {
             auto iw = m.host.find(conv + ".weight");
             auto g = m.host.find(bn + ".weight"), bb = m.host.find(bn + ".bias"), mu = m.host.find(bn + ".running_mean"),
                  var = m.host.find(bn + ".running_var");
             if (iw == m.host.end() || g == m.host.end() || bb == m.host.end() || mu == m.host.end() || var == m.host.end()) return false;
             const HostTensor& W = iw->second;
-            if (W.shape.size() != 4 || W.shape[0] != 256 || W.shape[1] != 64 || W.shape[2] != 1 || W.shape[3] != 1) return false;
-            w.resize(256 * 64); beta.resize(256);
-            for (int o = 0; o < 256; ++o) {
+            if (W.shape.size() != 4 || W.shape[0] != cout || W.shape[1] != cin || W.shape[2] != 1 || W.shape[3] != 1) return false;
+            w.resize((size_t)cout * cin); beta.resize(cout);
+            for (int o = 0; o < cout; ++o) {
                 const float invstd = 1.0f / std::sqrt(var->second.data[o] + 1e-5f);          // as pack_conv folds it
                 const float alpha = g->second.data[o] * invstd;
                 beta[o] = bb->second.data[o] - mu->second.data[o] * alpha;
-                for (int c = 0; c < 64; ++c) w[o * 64 + c] = W.data[o * 64 + c] * alpha;
+                for (int c = 0; c < cin; ++c) w[(size_t)o * cin + c] = W.data[(size_t)o * cin + c] * alpha;
             }
             return true;
         };
         std::vector<float> w3, b3, wd, bd;
-        if (fold(p + ".conv3", p + ".bn3", w3, b3) && fold(p + ".downsample.0", p + ".downsample.1", wd, bd)) {
-            HostTensor cat;
-            cat.shape = {256, 128, 1, 1};
-            cat.data.resize(256 * 128);
-            std::vector<float> one(256, 1.f), shift(256);
-            for (int o = 0; o < 256; ++o) {
-                for (int c = 0; c < 64; ++c) { cat.data[o * 128 + c] = w3[o * 64 + c]; cat.data[o * 128 + 64 + c] = wd[o * 64 + c]; }
-                shift[o] = b3[o] + bd[o];
-            }
-            m.host[p + ".conv3d.weight"] = std::move(cat);
-            int st = pack_conv(ctx, m, {p + ".conv3d"}, "", p + ".conv3d", one.data(), shift.data());
-            m.host.erase(p + ".conv3d.weight");
-            FCP_TRY(st);
+        if (!fold(p + ".conv3", p + ".bn3", cin3, w3, b3) || !fold(p + ".downsample.0", p + ".downsample.1", cind, wd, bd)) continue;
+        HostTensor cat;
+        const int K = cin3 + cind;
+        cat.shape = {cout, K, 1, 1};
+        cat.data.resize((size_t)cout * K);
+        std::vector<float> one(cout, 1.f), shift(cout);
+        for (int o = 0; o < cout; ++o) {
+            for (int c = 0; c < cin3; ++c) cat.data[(size_t)o * K + c] = w3[(size_t)o * cin3 + c];
+            for (int c = 0; c < cind; ++c) cat.data[(size_t)o * K + cin3 + c] = wd[(size_t)o * cind + c];
+            shift[o] = b3[o] + bd[o];
         }
+        m.host[p + ".conv3d.weight"] = std::move(cat);
+        int st = pack_conv(ctx, m, {p + ".conv3d"}, "", p + ".conv3d", one.data(), shift.data());
+        m.host.erase(p + ".conv3d.weight");
+        FCP_TRY(st);
     }
     for (const char* n : {"fpn.output1", "fpn.output2", "fpn.output3", "fpn.merge1", "fpn.merge2"})
         FCP_TRY(pack_conv(ctx, m, {std::string(n) + ".0"}, std::string(n) + ".1", n));
@@ -188,11 +189,20 @@ static Tensor bottleneck(Exec& ex, const std::string& p, Tensor x, int planes, i
     ex.conv(p + ".conv2", t1, t2, stride, 1, FCP_ACT_RELU);
     ex.free(t1);
     Tensor sc = x;
-    if (down) {
+    // tensor-core routes: the shortcut conv is folded into conv3 (finalize_retinaface) - x is conv3's second K source
+    const bool folded = down && ex.ctx->use_tc >= 1 && ex.model->conv.count(p + ".conv3d") && !getenv("FCP_NO_FUSE_SHORTCUT");
+    if (down && !folded) {
         sc = ex.alloc(x.n, ho, wo, planes * 4);
         ex.conv(p + ".downsample", x, sc, stride, 0, FCP_ACT_NONE);
     }
     Tensor out = ex.alloc(x.n, ho, wo, planes * 4);
+    if (folded) {
+        ConvOp e;
+        e.in2 = x; e.in2_stride = stride;
+        ex.conv(p + ".conv3d", t2, out, 1, 0, FCP_ACT_RELU, e);
+        ex.free(t2);
+        return out;
+    }
     ex.conv(p + ".conv3", t2, out, 1, 0, FCP_ACT_RELU, with_res1(sc));
     ex.free(t2);
     if (down) ex.free(sc);
@@ -220,27 +230,13 @@ static int retinaface_forward(Exec& ex, const uint8_t* images, int nb, int h, in
     if (!stem) return ex.status;
     Tensor s1 = ex.alloc(nb, odim(h, 7, 2, 3), odim(w, 7, 2, 3), 64);
     stem7(ex, "body.conv1", images, 0, nb, h, w, s1);
-    // tensor-core routes: layer1.0 runs conv3 + shortcut conv as one conv over [h | x] (finalize_retinaface): the pooled
-    // stem output x and the block's 3x3 output h share one 128-channel tensor
-    const bool fuse10 = ex.ctx->use_tc >= 1 && ex.model->conv.count("body.layer1.0.conv3d") && !getenv("FCP_NO_FUSE_SHORTCUT");
-    Tensor cat10 = ex.alloc(nb, odim(s1.h, 3, 2, 1), odim(s1.w, 3, 2, 1), fuse10 ? 128 : 64);
-    Tensor x = fuse10 ? cat10.slice(64, 64) : cat10;
+    Tensor x = ex.alloc(nb, odim(s1.h, 3, 2, 1), odim(s1.w, 3, 2, 1), 64);
     if (ex.ok() && !ex.dry) ex.status = launch_maxpool3s2(ex.ctx, s1, x);
     ex.free(s1);
     const int blocks[4] = {3, 4, 6, 3}, planes[4] = {64, 128, 256, 512};
     Tensor feats[3];
-    if (fuse10) {
-        Tensor t1 = ex.alloc(nb, x.h, x.w, 64);
-        ex.conv("body.layer1.0.conv1", x, t1, 1, 0, FCP_ACT_RELU);
-        ex.conv("body.layer1.0.conv2", t1, cat10.slice(0, 64), 1, 1, FCP_ACT_RELU);
-        ex.free(t1);
-        Tensor y = ex.alloc(nb, x.h, x.w, 256);
-        ex.conv("body.layer1.0.conv3d", cat10, y, 1, 0, FCP_ACT_RELU);
-        ex.free(cat10);
-        x = y;
-    }
     for (int li = 1; li <= 4; ++li) {
-        for (int b = (li == 1 && fuse10) ? 1 : 0; b < blocks[li - 1]; ++b) {
+        for (int b = 0; b < blocks[li - 1]; ++b) {
             Tensor y = bottleneck(ex, "body.layer" + std::to_string(li) + "." + std::to_string(b), x, planes[li - 1],
                                   (b == 0 && li > 1) ? 2 : 1, b == 0);
             // the input of layer3.0 / layer4.0 is C3 / C4, still needed by the FPN; every other block input dies here

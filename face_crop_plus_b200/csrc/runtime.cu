@@ -342,7 +342,7 @@ DevOut::~DevOut() {
 int run_conv(fcp_ctx* ctx, const ConvOp& op) {
     const bool tc = op.impl >= 1 && conv_tc_supported(op);   // shapes the tensor-core kernel does not cover use the CUDA-core kernel
     if (!tc && !op.wt->w_kn) return fail(ctx, FCP_ERR_INVALID, "conv: this packing exists for the tensor-core kernel only");
-    if (!tc && (op.act_cols < op.wt->cout || op.out_add))
+    if (!tc && (op.act_cols < op.wt->cout || op.out_add || op.in2.p))
         return fail(ctx, FCP_ERR_INVALID, "conv: a partial activation / accumulating output needs the tensor-core kernel");
     static const bool log_conv = getenv("FCP_LOG_CONV") != nullptr;      // one line per tensor-core launch, in launch order:
     if (log_conv && tc) {                                                  // lets an ncu capture (-k conv_tc -s N) be matched to layer shapes
