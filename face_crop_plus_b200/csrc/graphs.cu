@@ -190,7 +190,9 @@ static Tensor bottleneck(Exec& ex, const std::string& p, Tensor x, int planes, i
     ex.free(t1);
     Tensor sc = x;
     // tensor-core routes: the shortcut conv is folded into conv3 (finalize_retinaface) - x is conv3's second K source
-    const bool folded = down && ex.ctx->use_tc >= 1 && ex.model->conv.count(p + ".conv3d") && !getenv("FCP_NO_FUSE_SHORTCUT");
+    // (maps under 64 pixels run on the CUDA-core kernel, which has no second source: conv_tc_supported)
+    const bool folded = down && ex.ctx->use_tc >= 1 && (size_t)ho * wo >= 64 && ex.model->conv.count(p + ".conv3d") &&
+                        !getenv("FCP_NO_FUSE_SHORTCUT");
     if (down && !folded) {
         sc = ex.alloc(x.n, ho, wo, planes * 4);
         ex.conv(p + ".downsample", x, sc, stride, 0, FCP_ACT_NONE);
