@@ -124,12 +124,14 @@ def measured_peaks():
 
 
 def committed_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` summary (profiles/r2_traffic.json)."""
-    p = REPO / "profiles" / "r2_traffic.json"
-    try:
-        return json.loads(p.read_text())
-    except (OSError, ValueError):
-        return None
+    """DRAM bytes per launch of the dominant kernel from the committed ncu launch list of the newest build that has one
+    (profiles/r2b_traffic.json, else profiles/r2_traffic.json)."""
+    for name in ("r2b_traffic.json", "r2_traffic.json"):
+        try:
+            return json.loads((REPO / "profiles" / name).read_text())
+        except (OSError, ValueError):
+            continue
+    return None
 
 
 # ------------------------------------------------------------------------------------------------ CPU baselines
