@@ -251,3 +251,24 @@ def test_detector_stem_direct_uint8_route_equals_row_patch_route(ctx):
         scale = float(np.abs(ffma).max())
         print(f"stem routes {h}x{w}: |direct - rows| {np.abs(direct - rows).max():.2e}, |direct - cuda-core| {np.abs(direct - ffma).max():.2e} (|heads| max {scale:.1f})")
         assert np.abs(direct - rows).max() < 2e-4 and np.abs(direct - ffma).max() < 5e-4
+
+
+def test_detector_folded_shortcut_convs_equal_unfolded_graph(ctx):
+    """Tensor-core routes fold the shortcut conv of each ResNet-50 block 0 into conv3 (second K source of the conv kernel,
+    graphs.cu `bottleneck`).  Against the unfolded graph on the same kernel (FCP_NO_FUSE_SHORTCUT=1) the heads must agree
+    to float noise - also where the last stage's map is under 64 pixels and stays unfolded, and on odd map sizes (the
+    stride-2 sampling of the block input must line up with the 3x3/2 conv's output grid)."""
+    import os
+    for h, w in ((256, 320), (136, 208), (250, 314)):
+        imgs = synth.make_images(2, h, w, seed=90 + h)
+        folded = ctx.detect_heads(imgs)
+        os.environ["FCP_NO_FUSE_SHORTCUT"] = "1"
+        try:
+            plain = ctx.detect_heads(imgs)
+        finally:
+            del os.environ["FCP_NO_FUSE_SHORTCUT"]
+        d = float(np.abs(folded - plain).max())
+        print(f"folded vs unfolded shortcuts {h}x{w}: {d:.2e} (|heads| max {float(np.abs(plain).max()):.1f})")
+        assert np.isfinite(folded).all() and d < 2e-4
+        if (h, w) == (256, 320):
+            assert not np.array_equal(folded, plain)        # the switch really selects another graph
