@@ -80,3 +80,15 @@ def test_parse_landmarks_csv_skips_header(tmp_path):
     p.write_text("name,x1,y1,x2,y2,x3,y3,x4,y4,x5,y5\na.jpg,1,2,3,4,5,6,7,8,9,10\nb.jpg,10,9,8,7,6,5,4,3,2,1\n")
     lms, names = utils.parse_landmarks_file(str(p))
     assert lms.shape == (2, 5, 2) and names.tolist() == ["a.jpg", "b.jpg"] and lms[0, 4].tolist() == [9, 10]
+
+
+def test_bench_roofline_traffic_comes_from_a_committed_ncu_summary():
+    """bench.py's roofline.traffic is read from the committed ncu launch-list summary of the newest build that has one."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+    import bench
+    t = bench.committed_traffic()
+    assert t and t["kernel"] == "conv_tc_kernel" and t["launches"] > 100
+    assert 0.5 < t["dram_bytes_per_launch"] / t["algorithmic_bytes_per_launch"] < 1.5
+    assert (Path(bench.REPO) / "profiles" / "r2b_launches_dram.txt").exists()
