@@ -59,6 +59,8 @@ struct ConvOp {
     int up_in = 0;             // read the input through a nearest x2 upsample (logical size = 2x physical)
     int act = FCP_ACT_NONE;
     float slope = 0.f;
+    int out_rs = 0; size_t out_is = 0;   // != 0: row / image stride of `out` in floats when they are not w*cs / h*w*cs (a strided output view:
+                               // RRDBNet's upsampling convs write one output-pixel parity class each; tensor-core kernel, TMA epilogue only)
     int out_add = 0;           // out += result instead of out = result (tensor-core kernel with the TMA epilogue only; RRDB skip, graphs.cu)
     int act_cols = 1 << 30;    // the activation applies to output channels < act_cols only (tcgen05 kernel; RRDBNet source-major passes)
     const float* res1 = nullptr; int res1_cs = 0, res1_co = 0;              // added before the activation

@@ -1107,6 +1107,10 @@ int launch_conv_tc(fcp_ctx* ctx, const ConvOp& op) {
         if ((H + 6 - 7) / 2 + 1 != p.Ho || (W + 6 - 7) / 2 + 1 != p.Wo || op.out.c != 64) return fail(ctx, FCP_ERR_INVALID, "stem: output shape mismatch");
         p.KH = 4; p.KW = 1; p.Cin = 64; p.stride = p.stride_w = 1; p.pad = p.pad_w = 0;
         p.stem = 1; p.stem_H = H; p.stem_W = W;
+    } else if (op.out_rs) {
+        // parity class of an upsampling conv: 2x2 taps, `pad` rows/columns of zero padding BEFORE and 1 - pad after -> same size
+        if (p.KH != 2 || p.KW != 2 || p.stride != 1 || p.stride_w != 1 || p.Ho != H || p.Wo != W || (unsigned)p.pad > 1u || (unsigned)p.pad_w > 1u)
+            return fail(ctx, FCP_ERR_INVALID, "conv: a strided output view takes a 2x2 stride-1 same-size conv");
     } else if ((H + 2 * p.pad - p.KH) / p.stride + 1 != p.Ho || (W + 2 * p.pad_w - p.KW) / p.stride_w + 1 != p.Wo)
         return fail(ctx, FCP_ERR_INVALID, "conv: output shape mismatch");
     // spatial box of 128 output pixels: widest power-of-two width that does not overshoot the row by more than 2x
@@ -1187,16 +1191,18 @@ int launch_conv_tc(fcp_ctx* ctx, const ConvOp& op) {
     {
         const int bws = BW, bhs = BH;
         auto tensor_ok = [](const float* base, int cs) { return cs % 4 == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0; };
-        auto epi_map = [&](CUtensorMap* map, const float* base, int cs) {
+        auto epi_map = [&](CUtensorMap* map, const float* base, int cs, size_t rs = 0, size_t is = 0) {
             cuuint64_t dims[4] = {(cuuint64_t)wt.cout, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)p.N};
-            cuuint64_t strides[3] = {(cuuint64_t)cs * 4, (cuuint64_t)p.Wo * cs * 4, (cuuint64_t)p.Ho * p.Wo * cs * 4};
+            cuuint64_t strides[3] = {(cuuint64_t)cs * 4, (cuuint64_t)(rs ? rs : (size_t)p.Wo * cs) * 4,
+                                     (cuuint64_t)(is ? is : (size_t)p.Ho * p.Wo * cs) * 4};
             cuuint32_t box[4] = {32, (cuuint32_t)bws, (cuuint32_t)bhs, 1};
             return make_map(map, const_cast<float*>(base), 4, dims, strides, box);
         };
         p.out_tma = !op.res3 && tensor_ok(op.out.p + op.out.co, op.out.cs) && getenv("FCP_TC_NO_TMA_EPI") == nullptr;
-        if (p.out_tma && !epi_map(&p.tmOut, op.out.p + op.out.co, op.out.cs))
+        if (p.out_tma && !epi_map(&p.tmOut, op.out.p + op.out.co, op.out.cs, (size_t)op.out_rs, op.out_is))
             return fail(ctx, FCP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the output tensor");
-        if (op.out_add && !p.out_tma) return fail(ctx, FCP_ERR_INVALID, "conv_tc: out_add needs the TMA epilogue");
+        if ((op.out_add || op.out_rs || op.out_is) && !p.out_tma)
+            return fail(ctx, FCP_ERR_INVALID, "conv_tc: out_add / a strided output view need the TMA epilogue");
         const float* rsrc = op.res1 ? op.res1 : op.res2;
         const int r_cs = op.res1 ? op.res1_cs : op.res2_cs, r_co = op.res1 ? op.res1_co : op.res2_co;
         p.res_tma = rsrc && !(op.res2 && op.res2_h) && tensor_ok(rsrc + r_co, r_cs) && getenv("FCP_TC_NO_TMA_EPI") == nullptr;

@@ -427,6 +427,41 @@ int finalize_rrdbnet(fcp_ctx* ctx) {
                 FCP_TRY(pack_conv(ctx, m, {p}, "", p));
             }
     for (const char* c : {"trunk_conv", "upconv1", "upconv2", "HRconv", "conv_last"}) FCP_TRY(pack_conv(ctx, m, {c}, "", c));
+    // ---- upconv1 / upconv2 on a nearest x2 upsampled input (rrdb.py:78-79): output pixel (2y+py, 2x+px) only ever sees the
+    // low-resolution pixels (y-1+py .. y+py) x (x-1+px .. x+px), because pairs of the 3x3 taps land on the same source pixel.
+    // Per output parity class the conv is therefore a 2x2 conv on the LOW-resolution tensor whose weights are sums of the
+    // original taps (rows: py = 0 -> {w0, w1 + w2}, py = 1 -> {w0 + w1, w2}; columns alike): 4/9 of the MMAs and no
+    // materialised upsample.  rrdbnet_forward runs the four classes as four launches into strided views of the output.
+    for (const char* name : {"upconv1", "upconv2"}) {
+        auto iw = m.host.find(std::string(name) + ".weight");
+        auto ib = m.host.find(std::string(name) + ".bias");
+        if (iw == m.host.end() || iw->second.shape.size() != 4 || iw->second.shape[0] != 64 || iw->second.shape[1] != 64 ||
+            iw->second.shape[2] != 3 || iw->second.shape[3] != 3)
+            continue;
+        const std::vector<float>& W = iw->second.data;
+        std::vector<float> one(64, 1.f), bias(64, 0.f);
+        if (ib != m.host.end())
+            for (int o = 0; o < 64; ++o) bias[o] = ib->second.data[o];
+        for (int py = 0; py < 2; ++py)
+            for (int px = 0; px < 2; ++px) {
+                HostTensor w2;
+                w2.shape = {64, 64, 2, 2};
+                w2.data.assign((size_t)64 * 64 * 4, 0.f);
+                for (int o = 0; o < 64; ++o)
+                    for (int c = 0; c < 64; ++c)
+                        for (int r = 0; r < 3; ++r)
+                            for (int t = 0; t < 3; ++t) {
+                                const int r2 = (r + 1 - py) >> 1, t2 = (t + 1 - px) >> 1;      // the 2x2 tap the 3x3 tap falls on
+                                w2.data[(((size_t)o * 64 + c) * 2 + r2) * 2 + t2] += W[(((size_t)o * 64 + c) * 3 + r) * 3 + t];
+                            }
+                const std::string full = std::string(name) + ".p" + std::to_string(py) + std::to_string(px);
+                m.host[full + ".weight"] = std::move(w2);
+                int st = pack_conv(ctx, m, {full}, "", full, one.data(), bias.data());
+                m.host.erase(full + ".weight");
+                FCP_TRY(st);
+                m.conv[full].alg_k = 9 * 64;            // FLOP accounting: a quarter of the reference's 3x3 conv per class
+            }
+    }
     // ---- conv_last (64 -> 3) for the direct fp32 kernel (misc.cu conv3_last_kernel): [tap][cin][cout] + bias
     {
         auto iw = m.host.find("conv_last.weight");
@@ -576,11 +611,30 @@ static int rrdbnet_forward(Exec& ex, const std::function<int(Tensor)>& fill_firs
     ex.free(first);
     ConvOp up;
     up.up_in = 1; up.slope = 0.2f;
+    // tensor-core routes: four 2x2 convs on the low-resolution input, one per output-pixel parity class (finalize_rrdbnet)
+    auto upconv = [&](const std::string& name, Tensor lo, Tensor hi) {
+        const bool classes = ex.ctx->use_tc >= 1 && (size_t)lo.h * lo.w >= 64 && ex.model->conv.count(name + ".p00") &&
+                             !getenv("FCP_UPCONV_MATERIALIZE");
+        if (!classes) { ex.conv(name, lo, hi, 1, 1, FCP_ACT_LRELU, up); return; }
+        for (int py = 0; py < 2; ++py)
+            for (int px = 0; px < 2; ++px) {
+                ConvOp o;
+                o.slope = 0.2f;
+                o.pad_w = px == 0 ? 1 : 0;                                      // taps (y - 1 + py .. y + py) x (x - 1 + px .. x + px)
+                Tensor view = hi;                                               // output pixel (y, x) of the class -> (2y + py, 2x + px)
+                view.h = lo.h; view.w = lo.w;
+                view.cs = 2 * hi.cs;
+                view.co = hi.co + (py * hi.w + px) * hi.cs;
+                o.out_rs = 2 * hi.w * hi.cs;
+                o.out_is = (size_t)hi.h * hi.w * hi.cs;
+                ex.conv(name + ".p" + std::to_string(py) + std::to_string(px), lo, view, 1, py == 0 ? 1 : 0, FCP_ACT_LRELU, o);
+            }
+    };
     Tensor u1 = ex.alloc(nb, 2 * h, 2 * w, 64);
-    ex.conv("upconv1", fea, u1, 1, 1, FCP_ACT_LRELU, up);
+    upconv("upconv1", fea, u1);
     ex.free(fea);
     Tensor u2 = ex.alloc(nb, 4 * h, 4 * w, 64);
-    ex.conv("upconv2", u1, u2, 1, 1, FCP_ACT_LRELU, up);
+    upconv("upconv2", u1, u2);
     ex.free(u1);
     ConvOp lre;
     lre.slope = 0.2f;

@@ -342,7 +342,7 @@ DevOut::~DevOut() {
 int run_conv(fcp_ctx* ctx, const ConvOp& op) {
     const bool tc = op.impl >= 1 && conv_tc_supported(op);   // shapes the tensor-core kernel does not cover use the CUDA-core kernel
     if (!tc && !op.wt->w_kn) return fail(ctx, FCP_ERR_INVALID, "conv: this packing exists for the tensor-core kernel only");
-    if (!tc && (op.act_cols < op.wt->cout || op.out_add || op.in2.p))
+    if (!tc && (op.act_cols < op.wt->cout || op.out_add || op.in2.p || op.out_rs || op.out_is))
         return fail(ctx, FCP_ERR_INVALID, "conv: a partial activation / accumulating output needs the tensor-core kernel");
     static const bool log_conv = getenv("FCP_LOG_CONV") != nullptr;      // one line per tensor-core launch, in launch order:
     if (log_conv && tc) {                                                  // lets an ncu capture (-k conv_tc -s N) be matched to layer shapes
@@ -368,7 +368,7 @@ int run_conv(fcp_ctx* ctx, const ConvOp& op) {
     const double M = (double)op.out.n * op.out.h * op.out.w, K = w.alg_k ? (double)w.alg_k : (double)w.k * w.k * w.cin;
     ctx->prof_flops += 2.0 * M * w.cout * K;
     ctx->prof_bytes += (op.stem_src ? 3.0 * op.out.n * op.stem_h * op.stem_w : 4.0 * (double)op.in.pixels() * w.cin) + 4.0 * (M * w.cout + K * w.cout);
-    ctx->prof_recs.push_back({(int)M, w.cout, w.alg_k ? 3 : w.cin, w.k, op.stride, tc ? 1 : 0});   // stems: the reference's 7x7x3
+    ctx->prof_recs.push_back({(int)M, w.cout, w.alg_k == 147 ? 3 : w.cin, w.k, op.stride, tc ? 1 : 0});   // stems: the reference's 7x7x3
     return s;
 }
 
